@@ -1,0 +1,204 @@
+"""Coefficient callables shared by the oracle tests and the CUDA parity tests.
+
+Each factory takes the ``ufl``-like namespace to build with, so the SAME
+source text is evaluated by two independent back ends: ``oracle.npufl`` (numpy,
+the checker) and ``hommx_b200.ufl`` (symbolic -> CUDA, the product).  The
+expressions are the ones the reference's tests and examples use (file:line in
+each docstring, relative to /root/reference).
+"""
+import math
+
+
+def smooth_sin(ufl):
+    """examples/hmm.py:15-16, examples/hmm_3d.py:14-15, test_integration_poisson.py:244-245,484-485"""
+
+    def A(x, y):
+        return 1.1 + x[0] + ufl.sin(2 * ufl.pi * y[0])
+
+    return A
+
+
+def analytic1(ufl):
+    """test/integration/test_integration_poisson.py:124-125"""
+
+    def A(x, y):
+        return 1 / (2 + ufl.cos(2 * ufl.pi * y[0]))
+
+    return A
+
+
+def analytic2(ufl):
+    """test/integration/test_integration_poisson.py:149-150"""
+
+    def A(x, y):
+        return 0.33 + 0.15 * (ufl.sin(2 * ufl.pi * x[0]) + ufl.sin(2 * ufl.pi * y[0]))
+
+    return A
+
+
+def periodic_only(ufl):
+    """test/integration/test_integration_poisson.py:191-196"""
+
+    def A(x, y):
+        return 2.0 + ufl.sin(2 * ufl.pi * y[0])
+
+    return A
+
+
+def x_only(ufl):
+    """test/integration/test_integration_poisson.py:401-402"""
+
+    def A(x, y):
+        return 1.1 + x[0]
+
+    return A
+
+
+def laminate(ufl):
+    """examples/diffusion/laminate.py:101-102"""
+
+    def A(x, y):
+        return ufl.conditional(ufl.cos(2 * ufl.pi * y[0]) < 0, 5, 0.05)
+
+    return A
+
+
+def _circle(ufl, a, b, r=0.25):
+    """examples/diffusion/inclusion.py:107-114, examples/linear_elasticity/rotated_fibers.py:23-29"""
+    dx = ufl.acos(ufl.cos(2 * ufl.pi * (a - 1 / 2)))
+    dy = ufl.acos(ufl.cos(2 * ufl.pi * (b - 1 / 2)))
+    return (dx**2 + dy**2) < ((2 * ufl.pi) ** 2 * r**2)
+
+
+def inclusion(ufl):
+    """examples/diffusion/inclusion.py:117-118"""
+
+    def A(x, y):
+        return ufl.conditional(_circle(ufl, y[0], y[1]), 0.001, 0.1)
+
+    return A
+
+
+def full_tensor_2d(ufl):
+    """matrix-valued, x- and y-dependent, symmetric (not in the reference's tests; exercises as_matrix)"""
+
+    def A(x, y):
+        a00 = 1.1 + x[0] + ufl.sin(2 * ufl.pi * y[0])
+        a01 = 0.2 * ufl.cos(2 * ufl.pi * y[1])
+        a11 = 2 + ufl.sin(2 * ufl.pi * (y[0] + y[1]))
+        return ufl.as_matrix([[a00, a01], [a01, a11]])
+
+    return A
+
+
+def full_tensor_3d(ufl):
+    def A(x, y):
+        a = 1.5 + x[1] + ufl.sin(2 * ufl.pi * y[0]) * ufl.cos(2 * ufl.pi * y[2])
+        b = 2.0 + 0.5 * ufl.cos(2 * ufl.pi * y[1])
+        c = 1.0 + 0.3 * ufl.sin(2 * ufl.pi * (y[0] + y[1] + y[2]))
+        o = 0.1 * ufl.sin(2 * ufl.pi * y[1])
+        return ufl.as_matrix([[a, o, 0.05], [o, b, 0.0], [0.05, 0.0, c]])
+
+    return A
+
+
+# ---- stratification Jacobians (transposed): M[p, i] = d theta_i / d x_p ----
+def dtheta_test_stratified(ufl, theta_factor=0.2):
+    """test/integration/test_integration_poisson.py:498-508"""
+
+    def Dtheta(x):
+        arg_0 = ufl.pi / 2 * x[0]
+        arg_1 = ufl.pi / 2 * x[1]
+        f = theta_factor * ufl.cos(arg_0) * ufl.cos(arg_1)
+        df_dx0 = -theta_factor * (ufl.pi / 2) * ufl.sin(arg_0) * ufl.cos(arg_1)
+        df_dx1 = -theta_factor * (ufl.pi / 2) * ufl.cos(arg_0) * ufl.sin(arg_1)
+        return ufl.as_matrix(
+            [[1 - x[1] * df_dx0, f + x[0] * df_dx0], [-f - x[1] * df_dx1, 1 + x[0] * df_dx1]]
+        )
+
+    return Dtheta
+
+
+def dtheta_wavy(ufl):
+    """examples/diffusion/laminate.py:109-117 completed to a square matrix:
+    theta(x) = (x1 - sin 2 pi x0, x0)."""
+
+    def Dtheta(x):
+        return ufl.as_matrix([[-2 * ufl.pi * ufl.cos(2 * ufl.pi * x[0]), 1.0], [1.0, 0.0]])
+
+    return Dtheta
+
+
+def dtheta_inclusion(ufl):
+    """examples/diffusion/inclusion.py:128-134"""
+
+    def Dtheta(x):
+        D = ufl.as_matrix([[1, 0.5 * 2 * ufl.pi * ufl.cos(2 * ufl.pi * x[1])], [0, 1]])
+        return ufl.transpose(D)
+
+    return Dtheta
+
+
+def dtheta_rotation_3d(ufl, W=0.4):
+    """examples/linear_elasticity/rotated_fibers.py:41-63 completed to a square rotation about
+    the x1 axis by gamma(x1) = pi x1 / (2 W)."""
+
+    def Dtheta(x):
+        g = 1 / 2 * ufl.pi * x[1] / W
+        R = ufl.as_matrix(
+            [[ufl.cos(g), 0.0, -ufl.sin(g)], [0.0, 1.0, 0.0], [ufl.sin(g), 0.0, ufl.cos(g)]]
+        )
+        return ufl.transpose(R)
+
+    return Dtheta
+
+
+def dtheta_shear_3d(ufl):
+    def Dtheta(x):
+        return ufl.as_matrix(
+            [[1.0 + 0.2 * x[0], 0.3, 0.0], [-0.1, 1.1, 0.2 * ufl.sin(x[1])], [0.05, 0.0, 0.9 + 0.1 * x[2]]]
+        )
+
+    return Dtheta
+
+
+# ---- elasticity ----
+def hooke(ufl, dim, mu, lambda_):
+    """test/integration/test_integration_linear_elasticity.py:84-94,234-244;
+    examples/linear_elasticity/rotated_fibers.py:66-76"""
+
+    def A(x, y):
+        I = ufl.Identity(dim)
+        i, j, k, l = ufl.indices(4)
+        return ufl.as_tensor(
+            lambda_(x, y) * I[i, j] * I[k, l] + mu(x, y) * (I[i, k] * I[j, l] + I[i, l] * I[j, k]),
+            indices=(i, j, k, l),
+        )
+
+    return A
+
+
+def hooke_sin_2d(ufl):
+    """test_integration_linear_elasticity.py:78-82"""
+    return hooke(ufl, 2, lambda x, y: 5 + 4.5 * ufl.sin(2 * ufl.pi * y[0]), lambda x, y: 1.25)
+
+
+def hooke_const_3d(ufl):
+    """test_integration_linear_elasticity.py:228-232"""
+    return hooke(ufl, 3, lambda x, y: 1, lambda x, y: 1.25)
+
+
+def hooke_fibre_3d(ufl, mu_in=100, mu_out=0.001):
+    """examples/linear_elasticity/rotated_fibers.py:23-38"""
+    return hooke(
+        ufl, 3, lambda x, y: ufl.conditional(_circle(ufl, y[1], y[2]), mu_in, mu_out), lambda x, y: 1
+    )
+
+
+def hooke_smooth_3d(ufl):
+    return hooke(
+        ufl,
+        3,
+        lambda x, y: 2 + x[0] + ufl.sin(2 * ufl.pi * y[0]) * ufl.cos(2 * ufl.pi * y[1]),
+        lambda x, y: 1.25 + 0.5 * ufl.cos(2 * ufl.pi * y[2]),
+    )
