@@ -1,0 +1,389 @@
+"""Coefficient front-end: trace ``A(x, y)`` / ``Dtheta_transpose(x)`` and emit
+the CUDA coefficient program the cell kernel evaluates on the fly.
+
+Replaces, for the hot path, what the reference gets from UFL + FFCx JIT:
+``self._A_micro = self._coeff(self._x_macro, self._y)`` and the
+``1 + n_b + n_b^2`` ``fem.form`` compilations
+(/root/reference/src/hommx/hmm.py:198, 259-274, 306, 756-757, 1015-1016).
+
+Because P1 gradients are constant per micro element, the operator depends on
+the coefficient only through its per-element quadrature mean.
+The tracer therefore splits every tensor component into
+
+    A_c(x, y) = c0_c(x) + sum_k c_ck(x) * s_k(x, y)
+
+where the *atoms* ``s_k`` are the distinct y-dependent scalar sub-expressions
+(e.g. only ``mu(y)`` for an isotropic Hooke tensor with constant lambda).  The
+kernel stores ``NATOMS`` doubles per micro element instead of a full tensor,
+and x-only sub-expressions are hoisted into per-point constants ``pc``.
+"""
+from __future__ import annotations
+
+import hashlib
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import ufl
+from .ufl import Expr, Tensor
+
+POISSON, ELASTICITY = 0, 1
+
+
+def voigt_pairs(d):
+    """Unit-strain basis order: diagonal entries, then (0,1)[,(0,2),(1,2)]."""
+    return [(q, q) for q in range(d)] + ([(0, 1)] if d == 2 else [(0, 1), (0, 2), (1, 2)])
+
+
+@dataclass
+class CoefficientProgram:
+    dim: int
+    kind: int
+    stratified: bool
+    degree: int  # UFL-estimated quadrature degree of the cell-problem forms
+    natoms: int
+    npc: int
+    ncomp: int
+    scalar: bool  # Poisson: A is a scalar times the identity
+    source: str  # CUDA struct body (deterministic text; hashed by the library)
+    atoms: list = field(default_factory=list)
+    comps: list = field(default_factory=list)  # traced unique tensor components (Expr)
+    dtheta: list | None = None  # traced d*d Expr, row-major M[p][i]
+
+    @property
+    def key(self):
+        return hashlib.sha1(self.source.encode()).hexdigest()[:16]
+
+    @property
+    def n_rhs(self):
+        d = self.dim
+        return d if self.kind == POISSON else d * (d + 1) // 2
+
+    # host-side evaluation (tests, drop-in classes) ---------------------------
+    def eval_dtheta(self, x):
+        d = self.dim
+        if self.dtheta is None:
+            return np.eye(d)
+        env = {("x", k): float(x[k]) for k in range(3)}
+        return np.array([float(ufl.evaluate(e, env)) for e in self.dtheta]).reshape(d, d)
+
+
+# ----------------------------------------------------------------------------
+# tracing
+# ----------------------------------------------------------------------------
+def _numeric_equal(a: Expr, b: Expr, dim, rng):
+    if a.key == b.key:
+        return True
+    for _ in range(4):
+        env = {("x", k): rng.uniform(0.1, 0.9) for k in range(3)}
+        env.update({("y", k): rng.uniform(0.0, 1.0) for k in range(dim)})
+        va, vb = float(ufl.evaluate(a, env)), float(ufl.evaluate(b, env))
+        if abs(va - vb) > 1e-13 * max(1.0, abs(va), abs(vb)):
+            return False
+    return True
+
+
+def _trace_components(A, dim, kind):
+    x = ufl.Coordinate("x", 3)
+    y = ufl.Coordinate("y", dim)
+    val = A(x, y)
+    rng = np.random.default_rng(0)
+    if kind == POISSON:
+        if isinstance(val, Tensor):
+            if val.data.shape != (dim, dim):
+                raise ValueError(f"A must be a scalar or a {dim}x{dim} matrix, got shape {val.data.shape}")
+            for i in range(dim):
+                for j in range(i + 1, dim):
+                    if not _numeric_equal(val.data[i, j], val.data[j, i], dim, rng):
+                        raise NotImplementedError(
+                            "non-symmetric diffusion tensors need a non-symmetric Krylov method; "
+                            "the CUDA path solves the cell problems with PCG"
+                        )
+            comps = [val.data[i, j] for i in range(dim) for j in range(i, dim)]
+            return comps, False
+        a = Expr.wrap(val)
+        zero = Expr.const(0.0)
+        comps = [a if i == j else zero for i in range(dim) for j in range(i, dim)]
+        return comps, True
+    if not isinstance(val, Tensor) or val.data.shape != (dim,) * 4:
+        raise ValueError(f"elasticity needs a rank-4 tensor of shape {(dim,) * 4}")
+    T = val.data
+    pairs = voigt_pairs(dim)
+    for (i, j) in pairs:
+        for (k, l) in pairs:
+            ok = (
+                _numeric_equal(T[i, j, k, l], T[j, i, k, l], dim, rng)
+                and _numeric_equal(T[i, j, k, l], T[i, j, l, k], dim, rng)
+                and _numeric_equal(T[i, j, k, l], T[k, l, i, j], dim, rng)
+            )
+            if not ok:
+                raise NotImplementedError("the elasticity tensor must have minor and major symmetries")
+    m = len(pairs)
+    comps = [T[pairs[p] + pairs[q]] for p in range(m) for q in range(p, m)]
+    return comps, False
+
+
+def _trace_dtheta(Dtheta_transpose, dim):
+    x = ufl.Coordinate("x", 3)
+    M = Dtheta_transpose(x)
+    if not isinstance(M, Tensor) or M.data.shape != (dim, dim):
+        shape = getattr(getattr(M, "data", None), "shape", None)
+        raise ValueError(
+            f"Dtheta_transpose must return a {dim}x{dim} matrix (got {shape}); micro and macro "
+            "meshes have equal dimension (hmm.py:114-115)"
+        )
+    flat = [M.data[p, i] for p in range(dim) for i in range(dim)]
+    for e in flat:
+        if ufl.depends_on(e, "y"):
+            raise ValueError("Dtheta_transpose may only depend on the macro point x")
+    return flat
+
+
+# ----------------------------------------------------------------------------
+# affine decomposition in y-dependent atoms
+# ----------------------------------------------------------------------------
+def _affine(e: Expr, dep):
+    """-> (c0: Expr, {atom_key: (atom_expr, coef_expr)}) with x-only c0/coef."""
+    if not dep(e):
+        return e, {}
+    op = e.op
+    if op in ("add", "sub"):
+        c0a, la = _affine(e.args[0], dep)
+        c0b, lb = _affine(e.args[1], dep)
+        sgn = 1.0 if op == "add" else -1.0
+        out = dict(la)
+        for k, (atom, coef) in lb.items():
+            coef = coef if sgn > 0 else -coef
+            out[k] = (atom, out[k][1] + coef) if k in out else (atom, coef)
+        return (c0a + c0b if sgn > 0 else c0a - c0b), out
+    if op == "neg":
+        c0, l = _affine(e.args[0], dep)
+        return -c0, {k: (a, -c) for k, (a, c) in l.items()}
+    if op == "mul":
+        a, b = e.args
+        if not dep(a) or not dep(b):
+            s, t = (a, b) if not dep(a) else (b, a)
+            c0, l = _affine(t, dep)
+            return s * c0, {k: (at, s * c) for k, (at, c) in l.items()}
+    if op == "div" and not dep(e.args[1]):
+        c0, l = _affine(e.args[0], dep)
+        den = e.args[1]
+        return c0 / den, {k: (at, c / den) for k, (at, c) in l.items()}
+    return Expr.const(0.0), {e.key: (e, Expr.const(1.0))}
+
+
+# ----------------------------------------------------------------------------
+# CUDA emission
+# ----------------------------------------------------------------------------
+_FUN = {"sin": "sin", "cos": "cos", "tan": "tan", "acos": "acos", "asin": "asin", "atan": "atan",
+        "sqrt": "sqrt", "exp": "exp", "ln": "log", "abs": "fabs"}  # fmt: skip
+_INFIX = {"add": "+", "sub": "-", "mul": "*", "div": "/", "lt": "<", "gt": ">", "le": "<=", "ge": ">=",
+          "eq": "==", "ne": "!=", "and": "&&", "or": "||"}  # fmt: skip
+
+
+class _Emitter:
+    def __init__(self, symmap, prefix):
+        self.symmap = symmap  # (name, k) -> C expression
+        self.lines = []
+        self.memo = {}
+        self.prefix = prefix
+
+    def ref(self, e: Expr):
+        if e.key in self.memo:
+            return self.memo[e.key]
+        op = e.op
+        if op == "const":
+            v = e.value
+            r = repr(v) if v >= 0 else f"({v!r})"
+            if "e" not in r and "." not in r and "inf" not in r and "nan" not in r:
+                r += ".0"
+            self.memo[e.key] = r
+            return r
+        if op == "sym":
+            r = self.symmap[e.value]
+            self.memo[e.key] = r
+            return r
+        a = [self.ref(t) for t in e.args]
+        if op in _INFIX:
+            rhs = f"{a[0]} {_INFIX[op]} {a[1]}"
+        elif op in _FUN:
+            rhs = f"{_FUN[op]}({a[0]})"
+        elif op == "neg":
+            rhs = f"-{a[0]}"
+        elif op == "not":
+            rhs = f"!{a[0]}"
+        elif op == "min":
+            rhs = f"fmin({a[0]}, {a[1]})"
+        elif op == "max":
+            rhs = f"fmax({a[0]}, {a[1]})"
+        elif op == "cond":
+            rhs = f"{a[0]} ? {a[1]} : {a[2]}"
+        elif op == "pow":
+            p = e.args[1]
+            if p.is_const() and float(p.value).is_integer() and 1 <= p.value <= 4:
+                rhs = " * ".join([a[0]] * int(p.value))
+            else:
+                rhs = f"pow({a[0]}, {a[1]})"
+        else:
+            raise NotImplementedError(op)
+        name = f"{self.prefix}{len(self.lines)}"
+        ctype = "bool" if e.is_condition() else "double"
+        self.lines.append(f"    const {ctype} {name} = {rhs};")
+        self.memo[e.key] = name
+        return name
+
+
+def _hoist_point_constants(exprs, pcs):
+    """Replace maximal x-only non-constant sub-expressions by pc symbols."""
+    memo_dep = {}, {}, {}
+
+    def dep_y(e):  # varies within a point: micro coordinate, averaged atoms, strain
+        return any(ufl.depends_on(e, n, m) for n, m in zip(("y", "s", "e"), memo_dep))
+
+    memo_x = {}
+    dep_x = lambda e: ufl.depends_on(e, "x", memo_x)  # noqa: E731
+    cache = {}
+
+    def visit(e):
+        if e.key in cache:
+            return cache[e.key]
+        if e.op == "const":
+            r = e
+        elif not dep_y(e) and dep_x(e):
+            if e.key not in pcs:
+                pcs[e.key] = (len(pcs), e)
+            r = Expr("sym", (), ("pc", pcs[e.key][0]))
+        elif e.op == "sym":
+            r = e
+        else:
+            r = Expr(e.op, tuple(visit(a) for a in e.args), e.value)
+        cache[e.key] = r
+        return r
+
+    return [visit(e) for e in exprs]
+
+
+def _body(lines, outs, target):
+    out = list(lines)
+    for i, r in enumerate(outs):
+        out.append(f"    {target}[{i}] = {r};")
+    return "\n".join(out)
+
+
+def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
+    """Trace the reference-style callables and emit the coefficient program."""
+    if dim not in (2, 3):
+        raise ValueError("Topology should be 3D or 2D")  # hmm.py:104-105
+    comps, scalar = _trace_components(A, dim, kind)
+    degree = max(ufl.estimate_degree(c, {"x": 0, "y": 1}) for c in comps)
+    dth = _trace_dtheta(Dtheta_transpose, dim) if Dtheta_transpose is not None else None
+
+    memo_dep = {}
+    dep = lambda e: ufl.depends_on(e, "y", memo_dep)  # noqa: E731
+    atoms, atom_index = [], {}
+    affine = []
+    for c in comps:
+        c0, lin = _affine(c, dep)
+        terms = []
+        for k, (atom, coef) in lin.items():
+            if k not in atom_index:
+                atom_index[k] = len(atoms)
+                atoms.append(atom)
+            terms.append((atom_index[k], coef))
+        affine.append((c0, terms))
+    natoms = len(atoms)
+
+    # tensor components as expressions of s[k] with x-only coefficients
+    def comp_expr(c0, terms):
+        e = c0
+        for k, coef in terms:
+            e = e + coef * Expr("sym", (), ("s", k))
+        return e
+
+    tens = [comp_expr(c0, t) for c0, t in affine]
+    pcs = {}
+    atoms_h = _hoist_point_constants(atoms, pcs)
+    tens_h = _hoist_point_constants(tens, pcs)
+    npc = len(pcs)
+
+    sym_x = {("x", k): f"x[{k}]" for k in range(3)}
+    sym_y = {("y", k): f"y[{k}]" for k in range(dim)}
+    sym_pc = {("pc", k): f"pc[{k}]" for k in range(max(npc, 1))}
+    sym_s = {("s", k): f"s[{k}]" for k in range(max(natoms, 1))}
+
+    em = _Emitter(sym_x, "p")
+    pc_refs = [em.ref(e) for _, e in sorted(pcs.values(), key=lambda t: t[0])]
+    pc_body = _body(em.lines, pc_refs, "pc")
+
+    em = _Emitter({**sym_pc, **sym_y}, "a")
+    at_refs = [em.ref(e) for e in atoms_h]
+    at_body = _body(em.lines, at_refs, "s")
+
+    em = _Emitter({**sym_pc, **sym_s}, "t")
+    te_refs = [em.ref(e) for e in tens_h]
+    te_body = _body(em.lines, te_refs, "A")
+
+    m = len(voigt_pairs(dim))
+    if kind == ELASTICITY:
+        sym_e = {("e", k): f"e[{k}]" for k in range(m)}
+        em = _Emitter({**sym_pc, **sym_s, **sym_e}, "g")
+        idx = {}
+        n = 0
+        for p in range(m):
+            for q in range(p, m):
+                idx[(p, q)] = idx[(q, p)] = n
+                n += 1
+        sig = []
+        for p in range(m):
+            acc = Expr.const(0.0)
+            for q in range(m):
+                acc = acc + tens_h[idx[(p, q)]] * Expr("sym", (), ("e", q))
+            sig.append(em.ref(acc))
+        st_body = _body(em.lines, sig, "sig")
+    else:
+        st_body = "    (void)pc; (void)s; (void)e; (void)sig;"
+
+    if dth is not None:
+        em = _Emitter(sym_x, "m")
+        dt_body = _body(em.lines, [em.ref(e) for e in dth], "M")
+    else:
+        dt_body = "\n".join(
+            f"    M[{p * dim + i}] = {1.0 if p == i else 0.0};" for p in range(dim) for i in range(dim)
+        )
+
+    fn = "  __device__ __forceinline__ static void"
+    src = f"""// hommx_b200 coefficient program v1
+struct HMX_COEFF {{
+  static constexpr int DIM = {dim};
+  static constexpr int KIND = {kind};
+  static constexpr int STRATIFIED = {1 if dth is not None else 0};
+  static constexpr int NATOMS = {natoms};
+  static constexpr int NPC = {npc};
+  static constexpr int NCOMP = {len(comps)};
+  static constexpr int SCALAR = {1 if scalar else 0};
+  static constexpr int QDEG = {degree};
+{fn} point_consts(const double* __restrict__ x, double* __restrict__ pc) {{
+    (void)x; (void)pc;
+{pc_body}
+  }}
+{fn} atoms(const double* __restrict__ pc, const double* __restrict__ y, double* __restrict__ s) {{
+    (void)pc; (void)y; (void)s;
+{at_body}
+  }}
+{fn} tensor(const double* __restrict__ pc, const double* __restrict__ s, double* __restrict__ A) {{
+    (void)pc; (void)s;
+{te_body}
+  }}
+{fn} stress(const double* __restrict__ pc, const double* __restrict__ s, const double* __restrict__ e, double* __restrict__ sig) {{
+{st_body}
+  }}
+{fn} dtheta(const double* __restrict__ x, double* __restrict__ M) {{
+    (void)x;
+{dt_body}
+  }}
+}};
+"""
+    return CoefficientProgram(
+        dim=dim, kind=kind, stratified=dth is not None, degree=degree, natoms=natoms, npc=npc,
+        ncomp=len(comps), scalar=scalar, source=src, atoms=atoms, comps=comps, dtheta=dth,
+    )  # fmt: skip
