@@ -41,6 +41,7 @@ class CoefficientProgram:
     kind: int
     stratified: bool
     degree: int  # UFL-estimated quadrature degree of the cell-problem forms
+    ydep: int  # bit k set: some atom reads y[k]
     natoms: int
     npc: int
     ncomp: int
@@ -263,6 +264,16 @@ def _hoist_point_constants(exprs, pcs):
     return [visit(e) for e in exprs]
 
 
+def _reads(e, sym, _memo=None):
+    """True if the expression reads the symbol ``sym`` = (name, k)."""
+    _memo = {} if _memo is None else _memo
+    r = _memo.get(e.key)
+    if r is None:
+        r = e.value == sym if e.op == "sym" else any(_reads(a, sym, _memo) for a in e.args)
+        _memo[e.key] = r
+    return r
+
+
 def _body(lines, outs, target):
     out = list(lines)
     for i, r in enumerate(outs):
@@ -323,6 +334,31 @@ def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
     te_refs = [em.ref(e) for e in tens_h]
     te_body = _body(em.lines, te_refs, "A")
 
+    # affine coefficients: C[0*NCOMP + c] = c0_c(x), C[(1+k)*NCOMP + c] = c_ck(x)
+    aff = [c0 for c0, _ in affine]
+    for k in range(natoms):
+        for c0, terms in affine:
+            coef = Expr.const(0.0)
+            for kk, cf in terms:
+                if kk == k:
+                    coef = coef + cf
+            aff.append(coef)
+    aff_h = _hoist_point_constants(aff, pcs)
+    if len(pcs) != npc:  # a coefficient appeared only here: regenerate the pc program
+        npc = len(pcs)
+        sym_pc = {("pc", k): f"pc[{k}]" for k in range(max(npc, 1))}
+        em = _Emitter(sym_x, "p")
+        pc_refs = [em.ref(e) for _, e in sorted(pcs.values(), key=lambda t: t[0])]
+        pc_body = _body(em.lines, pc_refs, "pc")
+    em = _Emitter(sym_pc, "c")
+    af_body = _body(em.lines, [em.ref(e) for e in aff_h], "C")
+
+    ydep = 0
+    for a in atoms:
+        for k in range(dim):
+            if _reads(a, ("y", k)):
+                ydep |= 1 << k
+
     m = len(voigt_pairs(dim))
     if kind == ELASTICITY:
         sym_e = {("e", k): f"e[{k}]" for k in range(m)}
@@ -362,6 +398,7 @@ struct HMX_COEFF {{
   static constexpr int NCOMP = {len(comps)};
   static constexpr int SCALAR = {1 if scalar else 0};
   static constexpr int QDEG = {degree};
+  static constexpr int YDEP = {ydep};
 {fn} point_consts(const double* __restrict__ x, double* __restrict__ pc) {{
     (void)x; (void)pc;
 {pc_body}
@@ -374,6 +411,10 @@ struct HMX_COEFF {{
     (void)pc; (void)s;
 {te_body}
   }}
+{fn} tensor_affine(const double* __restrict__ pc, double* __restrict__ C) {{
+    (void)pc;
+{af_body}
+  }}
 {fn} stress(const double* __restrict__ pc, const double* __restrict__ s, const double* __restrict__ e, double* __restrict__ sig) {{
 {st_body}
   }}
@@ -384,6 +425,6 @@ struct HMX_COEFF {{
 }};
 """
     return CoefficientProgram(
-        dim=dim, kind=kind, stratified=dth is not None, degree=degree, natoms=natoms, npc=npc,
+        dim=dim, kind=kind, stratified=dth is not None, degree=degree, ydep=ydep, natoms=natoms, npc=npc,
         ncomp=len(comps), scalar=scalar, source=src, atoms=atoms, comps=comps, dtheta=dth,
     )  # fmt: skip

@@ -1,0 +1,252 @@
+// Shared pieces of the micro cell kernels: launch parameters, the Kuhn/Freudenthal
+// element tables of the structured periodic micro mesh, index helpers, block
+// reductions and the macro element epilogue.
+//
+// Geometry restated: the micro mesh is the unit box split into
+// NM^D cubes, each cut into D! simplices that all walk from the cube's origin corner
+// to the opposite corner along one axis at a time ("type" t = the order pi_t in which
+// the axes are walked).  Vertex a of a type-t simplex sits at offset
+//   P(t,a) = e_{pi(0)} + .. + e_{pi(a-1)}            (a = 0..D)
+// and the P1 gradients are  g_a = n (e_{pi(a-1)} - e_{pi(a)})  (terms with an index
+// outside 0..D-1 dropped), so d u / d y_{pi(k)} = n (u_{P(k+1)} - u_{P(k)}).
+// Periodicity (cell_problem.py:38-300 of the reference: every max-face node is a slave
+// of its wrapped image) is the index wrap i mod NM.
+#pragma once
+#include "hmx_platform.cuh"
+
+namespace hmx {
+
+struct CellParams {
+  long long n_pts;         // macro quadrature points (= macro cells in fused mode)
+  const double* x_pts;     // [n_pts][3] macro points, or nullptr when cells are given
+  const int* cell_nodes;   // [n_pts][D+1] macro cell vertex ids, or nullptr
+  const double* node_xyz;  // [n_nodes][3] macro vertex coordinates
+  double* A_hom;           // [n_pts][m*m] homogenised tensor (nullptr: not wanted)
+  double* S_loc;           // [n_pts][nb*nb] macro element matrices (nullptr: not wanted)
+  int* iters;              // [n_pts] PCG iterations (max over right-hand sides), or nullptr
+  double* resid;           // [n_pts] final relative residual (max over rhs), or nullptr
+  const double* qp;        // [T][nq][D] quadrature points, cube-local, in units of h
+  const double* qw;        // [nq] weights normalised to sum 1
+  double* scratch;         // per-CTA global scratch (elasticity: corrector vectors)
+  int nq;
+  int max_it;
+  double rtol, atol;
+};
+
+// ---- Kuhn tables ------------------------------------------------------------------
+template <int D>
+HMX_HOSTDEV constexpr int kuhn_ntypes() { return D == 2 ? 2 : 6; }
+
+// axis walked at step k of type t.  3-D order (matches the tetrahedra listed for
+// dolfinx create_box in SURVEY.md A.4): (x,y,z) (x,z,y) (z,x,y) (y,x,z) (z,y,x) (y,z,x)
+template <int D>
+HMX_HOSTDEV constexpr int kuhn_axis(int t, int k) {
+  if (D == 2) return t == 0 ? k : 1 - k;
+  constexpr unsigned long long packed = (36ULL) | (24ULL << 6) | (18ULL << 12) | (33ULL << 18) | (6ULL << 24) | (9ULL << 30);
+  return (int)((packed >> (6 * t + 2 * k)) & 3ULL);
+}
+// bit mask of the axes walked before vertex a
+template <int D>
+HMX_HOSTDEV constexpr int kuhn_pmask(int t, int a) {
+  int m = 0;
+  for (int k = 0; k < a; ++k) m |= 1 << kuhn_axis<D>(t, k);
+  return m;
+}
+
+HMX_HOSTDEV constexpr int ipow(int b, int e) { return e <= 0 ? 1 : b * ipow(b, e - 1); }
+HMX_HOSTDEV constexpr int popcount3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
+HMX_HOSTDEV constexpr int sym_index(int D, int i, int j) {  // upper triangle, row major
+  return i <= j ? i * D - i * (i - 1) / 2 + (j - i) : j * D - j * (j - 1) / 2 + (i - j);
+}
+
+template <int D, int NM>
+struct Grid {
+  static constexpr int N = ipow(NM, D);
+  HMX_DEV static void decode(int i, int (&c)[3]) {
+    c[0] = i % NM;
+    c[1] = (i / NM) % NM;
+    c[2] = D == 3 ? i / (NM * NM) : 0;
+  }
+  HMX_DEV static int up(int v) { return v + 1 == NM ? 0 : v + 1; }
+  HMX_DEV static int down(int v) { return v == 0 ? NM - 1 : v - 1; }
+  HMX_DEV static int index(int c0, int c1, int c2) { return D == 3 ? c0 + NM * (c1 + NM * c2) : c0 + NM * c1; }
+  // node at c + mask (sign=+1) or c - mask (sign=-1); mask has one bit per axis
+  template <int SIGN>
+  HMX_DEV static int shifted(const int (&c)[3], int mask) {
+    int s[3];
+    HMX_UNROLL
+    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a]) : down(c[a])) : c[a];
+    return index(s[0], s[1], s[2]);
+  }
+  template <int SIGN>
+  HMX_DEV static void shift_coords(const int (&c)[3], int mask, int (&s)[3]) {
+    HMX_UNROLL
+    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a]) : down(c[a])) : c[a];
+  }
+};
+
+// Atoms (the y-dependent scalars of the coefficient) are stored per element on the
+// REDUCED cube set: axes none of the atoms depend on are collapsed, so e.g. a laminate
+// a(y0) costs NM*T evaluations per macro point instead of NM^D*T.
+template <int D, int NM, int YDEP>
+struct AtomIdx {
+  static constexpr int NDEP = popcount3(YDEP & ((1 << D) - 1));
+  static constexpr int NRC = ipow(NM, NDEP);
+  HMX_DEV static int ridx(const int (&c)[3]) {
+    int r = 0, s = 1;
+    HMX_UNROLL
+    for (int a = 0; a < D; ++a)
+      if ((YDEP >> a) & 1) {
+        r += c[a] * s;
+        s *= NM;
+      }
+    return r;
+  }
+  HMX_DEV static void rdecode(int rc, int (&c)[3]) {
+    HMX_UNROLL
+    for (int a = 0; a < 3; ++a) {
+      c[a] = 0;
+      if (a < D && ((YDEP >> a) & 1)) {
+        c[a] = rc % NM;
+        rc /= NM;
+      }
+    }
+  }
+};
+
+// ---- block reductions ---------------------------------------------------------------
+// Sum NV values per thread over the CTA; every thread ends with the same totals (fixed
+// summation order -> deterministic).  One BAR.SYNC.  `buf` holds NW*NV doubles; callers
+// alternate between two buffers so that no trailing barrier is needed.
+template <int NV, int NW>
+HMX_DEV void block_sum(double (&v)[NV], double* buf) {
+  const int lane = tid() & 31, warp = tid() >> 5;
+  HMX_UNROLL
+  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+    HMX_UNROLL
+    for (int k = 0; k < NV; ++k) buf[warp * NV + k] = v[k];
+  }
+  sync();
+  HMX_UNROLL
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int w = 0; w < NW; ++w) s += buf[w * NV + k];
+    v[k] = s;
+  }
+}
+
+// ---- macro element epilogue -----------------------------------------------------------
+// P1 gradients of the macro simplex and |T| (hmm.py:20-28 of the reference), then
+//   S_loc[i][j] = |T| sum_pq C[p][j] A_hom[p][q] C[q][i]
+// with C[:,i] the gradient (Poisson) or engineering-Voigt strain (elasticity, unrolled
+// dof i = a*D + k, hmm.py:31-40) of macro basis function i  (SURVEY.md A.3).
+template <int D, int KIND>
+HMX_DEV void macro_element_matrix(const double* verts /* (D+1) x 3 */, const double* Ahom, double* S) {
+  constexpr int NV = D + 1;
+  constexpr int MV = KIND == 0 ? D : D * (D + 1) / 2;
+  constexpr int NB = KIND == 0 ? NV : NV * D;
+  double J[D][D];  // columns are edge vectors
+  HMX_UNROLL
+  for (int r = 0; r < D; ++r)
+    HMX_UNROLL
+    for (int c = 0; c < D; ++c) J[r][c] = verts[(c + 1) * 3 + r] - verts[r];
+  double Ji[D][D], det;
+  if (D == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double id = 1.0 / det;
+    Ji[0][0] = J[1][1] * id;
+    Ji[0][1] = -J[0][1] * id;
+    Ji[1][0] = -J[1][0] * id;
+    Ji[1][1] = J[0][0] * id;
+  } else {
+    const double c00 = J[1][1] * J[2 % D][2 % D] - J[1][2 % D] * J[2 % D][1];
+    const double c01 = J[1][2 % D] * J[2 % D][0] - J[1][0] * J[2 % D][2 % D];
+    const double c02 = J[1][0] * J[2 % D][1] - J[1][1] * J[2 % D][0];
+    det = J[0][0] * c00 + J[0][1] * c01 + J[0][2 % D] * c02;
+    const double id = 1.0 / det;
+    Ji[0][0] = c00 * id;
+    Ji[1][0] = c01 * id;
+    Ji[2 % D][0] = c02 * id;
+    Ji[0][1] = (J[0][2 % D] * J[2 % D][1] - J[0][1] * J[2 % D][2 % D]) * id;
+    Ji[1][1] = (J[0][0] * J[2 % D][2 % D] - J[0][2 % D] * J[2 % D][0]) * id;
+    Ji[2 % D][1] = (J[0][1] * J[2 % D][0] - J[0][0] * J[2 % D][1]) * id;
+    Ji[0][2 % D] = (J[0][1] * J[1][2 % D] - J[0][2 % D] * J[1][1]) * id;
+    Ji[1][2 % D] = (J[0][2 % D] * J[1][0] - J[0][0] * J[1][2 % D]) * id;
+    Ji[2 % D][2 % D] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+  }
+  const double vol = fabs(det) / (D == 2 ? 2.0 : 6.0);
+  // G[p][a] = d phi_a / d x_p : rows of J^-1 are the gradients of barycentric coords 1..D
+  double G[D][NV];
+  HMX_UNROLL
+  for (int p = 0; p < D; ++p) {
+    double s = 0.0;
+    HMX_UNROLL
+    for (int a = 1; a < NV; ++a) {
+      G[p][a] = Ji[a - 1][p];
+      s += Ji[a - 1][p];
+    }
+    G[p][0] = -s;
+  }
+  double C[MV][NB];
+  if (KIND == 0) {
+    HMX_UNROLL
+    for (int p = 0; p < D; ++p)
+      HMX_UNROLL
+      for (int a = 0; a < NV; ++a) C[p][a] = G[p][a];
+  } else {
+    HMX_UNROLL
+    for (int a = 0; a < NV; ++a)
+      HMX_UNROLL
+      for (int k = 0; k < D; ++k) {
+        const int i = a * D + k;
+        HMX_UNROLL
+        for (int q = 0; q < D; ++q) C[q][i] = (q == k) ? G[q][a] : 0.0;
+        int v = D;
+        HMX_UNROLL
+        for (int r = 0; r < D; ++r)
+          HMX_UNROLL
+          for (int c = r + 1; c < D; ++c) {
+            C[v][i] = ((r == k) ? G[c][a] : 0.0) + ((c == k) ? G[r][a] : 0.0);
+            ++v;
+          }
+      }
+  }
+  for (int i = 0; i < NB; ++i)
+    for (int j = 0; j < NB; ++j) {
+      double s = 0.0;
+      HMX_UNROLL
+      for (int p = 0; p < MV; ++p)
+        HMX_UNROLL
+        for (int q = 0; q < MV; ++q) s += C[p][j] * Ahom[p * MV + q] * C[q][i];
+      S[i * NB + j] = vol * s;
+    }
+}
+
+// macro point of unit `pt`: given directly, or the barycentre of the macro cell
+// (mean of the vertex coordinates, hmm.py:349-352)
+template <int D>
+HMX_DEV void macro_point(const CellParams& P, long long pt, double (&xm)[3], double (&verts)[(D + 1) * 3]) {
+  if (P.cell_nodes != nullptr) {
+    HMX_UNROLL
+    for (int k = 0; k < 3; ++k) xm[k] = 0.0;
+    HMX_UNROLL
+    for (int v = 0; v <= D; ++v) {
+      const long long node = P.cell_nodes[pt * (D + 1) + v];
+      HMX_UNROLL
+      for (int k = 0; k < 3; ++k) {
+        verts[v * 3 + k] = P.node_xyz[node * 3 + k];
+        xm[k] += verts[v * 3 + k];
+      }
+    }
+    HMX_UNROLL
+    for (int k = 0; k < 3; ++k) xm[k] /= (double)(D + 1);
+  } else {
+    HMX_UNROLL
+    for (int k = 0; k < 3; ++k) xm[k] = P.x_pts[pt * 3 + k];
+    HMX_UNROLL
+    for (int v = 0; v < (D + 1) * 3; ++v) verts[v] = 0.0;
+  }
+}
+
+}  // namespace hmx

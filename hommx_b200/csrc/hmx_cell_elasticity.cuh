@@ -1,0 +1,556 @@
+// Micro cell kernel for the linear-elasticity HMM classes: one CTA per macro quadrature point.
+//
+// Replaces, for LinearElasticityHMM / LinearElasticityStratifiedHMM, what the reference does in
+// BaseHMM._compute_local_stiffness (hmm.py:334-369) with the forms of hmm.py:887-922 /
+// 1024-1067: D(D+1)/2 unit-strain corrector problems instead of n_b = D(D+1).
+//
+// The periodic P1 stiffness matrix of the vector problem (D x D blocks on the 7-/15-point
+// stencil: 135 doubles per node in 3-D) does not fit in shared memory, so the operator is applied
+// MATRIX-FREE from the reference element kernel with the coefficient evaluated in place:
+//   per cube and right-hand side: gather the 2^D corner displacements, and per simplex
+//   H = n sum_k Mcol_{pi(k)} (x) (u_{P(k+1)} - u_{P(k)}),  e = sym(H)  (engineering Voigt),
+//   sigma = C(atoms of this element) : e   (generated `stress`, constant-folded for e.g. Hooke),
+//   t_k = |e| n sigma Mcol_{pi(k)};   y_{P(k+1)} += t_k,  y_{P(k)} -= t_k.
+// Cubes are processed colour by colour (2^D colours for even n) so that the in-place
+// accumulation into the shared-memory result needs no atomics and is deterministic.
+// Threads are grouped by right-hand side (NT = NRHS * TPR); search directions p and the product
+// y = K p live in shared memory, the residuals and correctors in an L2-resident per-CTA scratch.
+// Preconditioner: D x D block Jacobi.  Epilogue as in the Poisson kernel:
+//   A_hom[p][q] = <C>[p][q] - b_p.x_q - x_p.r_q.
+#pragma once
+#include "hmx_cell_common.cuh"
+
+namespace hmx {
+
+template <class CO, int NM, int NT>
+struct ElasticityLayout {
+  static constexpr int D = CO::DIM;
+  static constexpr int T = kuhn_ntypes<D>();
+  static constexpr int N = Grid<D, NM>::N;
+  static constexpr int NRHS = D * (D + 1) / 2;
+  static constexpr int NV = NRHS;  // Voigt length
+  static constexpr int NDOF = N * D;
+  static constexpr int TPR = NT / NRHS;  // threads per right-hand side
+  static constexpr int NW = NT / 32;
+  static constexpr int WPR = TPR / 32;  // warps per right-hand side
+  static constexpr int NA = CO::NATOMS;
+  static constexpr int NA1 = NA > 0 ? NA : 1;
+  static constexpr int NSYM = D * (D + 1) / 2;
+  static constexpr int NRC = AtomIdx<D, NM, CO::YDEP>::NRC;
+  static constexpr int NCOL = (NM % 2 == 0) ? 2 : 3;  // colours per axis
+  static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
+  static constexpr int o_red = 0;                              // 2 buffers [NW][NREDV]
+  static constexpr int o_atoms = o_red + 2 * NW * NREDV;       // [NA][T][NRC]
+  static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][N] inverse diagonal blocks
+  static constexpr int o_p = o_dinv + NSYM * N;                // [NRHS][D][N]
+  static constexpr int o_y = o_p + NRHS * NDOF;                // [NRHS][D][N]
+  static constexpr int total = o_y + NRHS * NDOF;
+  static constexpr int scratch_doubles = 2 * NRHS * NDOF;      // x and r per CTA
+  static_assert(NT % NRHS == 0 && TPR % 32 == 0, "block size must be NRHS * (multiple of 32)");
+};
+
+// inverse of a symmetric DxD matrix given by its upper triangle (row major)
+template <int D>
+HMX_DEV void sym_inverse(const double* a, double* inv) {
+  if (D == 2) {
+    const double det = a[0] * a[2] - a[1] * a[1];
+    const double id = det != 0.0 ? 1.0 / det : 0.0;
+    inv[0] = a[2] * id;
+    inv[1] = -a[1] * id;
+    inv[2] = a[0] * id;
+  } else {
+    // a = [a00 a01 a02 a11 a12 a22]
+    const double a00 = a[0], a01 = a[1], a02 = a[2 % (D * (D + 1) / 2)], a11 = a[3 % (D * (D + 1) / 2)],
+                 a12 = a[4 % (D * (D + 1) / 2)], a22 = a[5 % (D * (D + 1) / 2)];
+    const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+    const double det = a00 * c00 + a01 * c01 + a02 * c02;
+    const double id = det != 0.0 ? 1.0 / det : 0.0;
+    inv[0] = c00 * id;
+    inv[1] = c01 * id;
+    inv[2 % (D * (D + 1) / 2)] = c02 * id;
+    inv[3 % (D * (D + 1) / 2)] = (a00 * a22 - a02 * a02) * id;
+    inv[4 % (D * (D + 1) / 2)] = (a01 * a02 - a00 * a12) * id;
+    inv[5 % (D * (D + 1) / 2)] = (a00 * a11 - a01 * a01) * id;
+  }
+}
+
+// One sweep over the cubes: y += K p  (RHSMODE = false)  or  y += b_q  (RHSMODE = true: the
+// strain of every element is the unit strain E_q and the sign is flipped; hmm.py:898-903).
+template <class CO, int NM, int NT, bool RHSMODE>
+HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO::DIM], const double* s_atoms,
+                              const double* s_p, double* s_y, int q, int l) {
+  using L = ElasticityLayout<CO, NM, NT>;
+  using G = Grid<CO::DIM, NM>;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
+  constexpr int D = L::D, T = L::T, N = L::N, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC, NCOL = L::NCOL;
+  constexpr int NC = 1 << D;  // corners
+  constexpr int HALF = NM / 2;  // size of colour classes 0 and 1 (class 2, odd n only: the last index)
+  const double h = 1.0 / (double)NM;
+  const double w = (D == 2 ? 0.5 * h * h : h * h * h / 6.0);  // |e|; Mn already carries the factor n
+
+  for (int col = 0; col < ipow(NCOL, D); ++col) {
+    int cls[3], cnt[3], total = 1;
+    {
+      int r = col;
+      HMX_UNROLL
+      for (int a = 0; a < 3; ++a) {
+        cls[a] = a < D ? r % NCOL : 0;
+        if (a < D) r /= NCOL;
+        cnt[a] = a < D ? (cls[a] == 2 ? 1 : HALF) : 1;
+        total *= cnt[a];
+      }
+    }
+    for (int k = l; k < total; k += L::TPR) {
+      int o[3];
+      {
+        int r = k;
+        HMX_UNROLL
+        for (int a = 0; a < 3; ++a) {
+          const int idx = r % cnt[a];
+          r /= cnt[a];
+          o[a] = a < D ? (cls[a] == 2 ? NM - 1 : 2 * idx + cls[a]) : 0;
+        }
+      }
+      int node[NC];
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b) node[b] = G::template shifted<1>(o, b);
+      double u[NC][D], acc[NC][D];
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          acc[b][j] = 0.0;
+          u[b][j] = RHSMODE ? 0.0 : s_p[(q * D + j) * N + node[b]];
+        }
+      const int ro = AI::ridx(o);
+      HMX_UNROLL
+      for (int t = 0; t < T; ++t) {
+        double e[NV];
+        if (RHSMODE) {
+          HMX_UNROLL
+          for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -1.0 : 0.0;
+        } else {
+          // H[p][j] = sum_k Mn[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j])
+          double H[D][D];
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p)
+            HMX_UNROLL
+            for (int j = 0; j < D; ++j) H[p][j] = 0.0;
+          HMX_UNROLL
+          for (int k2 = 0; k2 < D; ++k2) {
+            const int ax = kuhn_axis<D>(t, k2);
+            const int b0 = kuhn_pmask<D>(t, k2), b1 = kuhn_pmask<D>(t, k2 + 1);
+            HMX_UNROLL
+            for (int j = 0; j < D; ++j) {
+              const double dk = u[b1][j] - u[b0][j];
+              HMX_UNROLL
+              for (int p = 0; p < D; ++p) H[p][j] += Mn[p * D + ax] * dk;
+            }
+          }
+          HMX_UNROLL
+          for (int v = 0; v < D; ++v) e[v] = H[v][v];
+          int v = D;
+          HMX_UNROLL
+          for (int r = 0; r < D; ++r)
+            HMX_UNROLL
+            for (int c = r + 1; c < D; ++c) {
+              e[v] = H[r][c] + H[c][r];
+              ++v;
+            }
+        }
+        double sa[NA1], sig[NV];
+        HMX_UNROLL
+        for (int k2 = 0; k2 < NA1; ++k2) sa[k2] = NA > 0 ? s_atoms[(k2 * T + t) * NRC + ro] : 0.0;
+        CO::stress(pc, sa, e, sig);
+        double S[D][D];
+        HMX_UNROLL
+        for (int v = 0; v < D; ++v) S[v][v] = w * sig[v];
+        {
+          int v = D;
+          HMX_UNROLL
+          for (int r = 0; r < D; ++r)
+            HMX_UNROLL
+            for (int c = r + 1; c < D; ++c) {
+              S[r][c] = S[c][r] = w * sig[v];
+              ++v;
+            }
+        }
+        HMX_UNROLL
+        for (int k2 = 0; k2 < D; ++k2) {
+          const int ax = kuhn_axis<D>(t, k2);
+          const int b0 = kuhn_pmask<D>(t, k2), b1 = kuhn_pmask<D>(t, k2 + 1);
+          HMX_UNROLL
+          for (int j = 0; j < D; ++j) {
+            double tk = 0.0;
+            HMX_UNROLL
+            for (int p = 0; p < D; ++p) tk += S[j][p] * Mn[p * D + ax];
+            acc[b1][j] += tk;
+            acc[b0][j] -= tk;
+          }
+        }
+      }
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) s_y[(q * D + j) * N + node[b]] += acc[b][j];
+    }
+    sync();
+  }
+}
+
+template <class CO, int NM, int NT>
+HMX_DEV void elasticity_cell_body(const CellParams& P) {
+  using L = ElasticityLayout<CO, NM, NT>;
+  using G = Grid<CO::DIM, NM>;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
+  constexpr int D = L::D, T = L::T, N = L::N, NRHS = L::NRHS, NV = L::NV, NDOF = L::NDOF, TPR = L::TPR, NW = L::NW;
+  constexpr int WPR = L::WPR, NA = L::NA, NA1 = L::NA1, NSYM = L::NSYM, NRC = L::NRC;
+  constexpr int NPT = (N + TPR - 1) / TPR;  // nodes per thread within its right-hand side
+  constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
+
+  double* sm = dyn_smem();
+  double* s_red = sm + L::o_red;
+  double* s_atoms = sm + L::o_atoms;
+  double* s_dinv = sm + L::o_dinv;
+  double* s_p = sm + L::o_p;
+  double* s_y = sm + L::o_y;
+  double* g_x = P.scratch + (size_t)bid() * L::scratch_doubles;  // [NRHS][D][N]
+  double* g_r = g_x + NRHS * NDOF;
+
+  const int t_id = tid();
+  const int q = t_id / TPR, l = t_id - q * TPR;
+  const int lane = t_id & 31, warp = t_id >> 5;
+  const double h = 1.0 / (double)NM;
+  const double vol = (D == 2 ? 0.5 * h * h : h * h * h / 6.0);
+  int red_flip = 0;
+
+  for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {
+    double xm[3], verts[(D + 1) * 3];
+    macro_point<D>(P, pt, xm, verts);
+    double pc[NPC1];
+    CO::point_consts(xm, pc);
+    double Mn[D * D];  // n * M,  M[p*D+i] = d theta_i / d x_p  (hmm.py:1015-1016)
+    CO::dtheta(xm, Mn);
+    HMX_UNROLL
+    for (int k = 0; k < D * D; ++k) Mn[k] *= (double)NM;
+
+    // ---- 1. atoms ----
+    if (NA > 0) {
+      for (int idx = t_id; idx < T * NRC; idx += NT) {
+        const int t = idx / NRC, rc = idx - t * NRC;
+        int c[3];
+        AI::rdecode(rc, c);
+        double acc[NA1];
+        HMX_UNROLL
+        for (int k = 0; k < NA1; ++k) acc[k] = 0.0;
+        for (int qq = 0; qq < P.nq; ++qq) {
+          double y[D], s[NA1];
+          HMX_UNROLL
+          for (int a = 0; a < D; ++a) y[a] = ((double)c[a] + P.qp[(t * P.nq + qq) * D + a]) * h;
+          CO::atoms(pc, y, s);
+          const double wq = P.qw[qq];
+          HMX_UNROLL
+          for (int k = 0; k < NA1; ++k) acc[k] += wq * s[k];
+        }
+        HMX_UNROLL
+        for (int k = 0; k < NA; ++k) s_atoms[(k * T + t) * NRC + rc] = acc[k];
+      }
+    }
+    // zero the accumulation target
+    for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;
+    sync();
+
+    // ---- 2. atom means, block-Jacobi preconditioner ----
+    double smean[NA1];
+    HMX_UNROLL
+    for (int k = 0; k < NA1; ++k) smean[k] = 0.0;
+    if (NA > 0) {
+      for (int idx = t_id; idx < T * NRC; idx += NT) {
+        HMX_UNROLL
+        for (int k = 0; k < NA; ++k) smean[k] += s_atoms[k * T * NRC + idx];
+      }
+      block_sum<NA1, NW>(smean, s_red + (red_flip ^= 1) * NW * L::NREDV);
+      HMX_UNROLL
+      for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * NRC);
+    }
+    for (int i = t_id; i < N; i += NT) {
+      int c[3];
+      G::decode(i, c);
+      double blk[NSYM];
+      HMX_UNROLL
+      for (int k = 0; k < NSYM; ++k) blk[k] = 0.0;
+      HMX_UNROLL
+      for (int t = 0; t < T; ++t) {
+        HMX_UNROLL
+        for (int a = 0; a <= D; ++a) {
+          int o[3];
+          G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
+          const int ro = AI::ridx(o);
+          double sa[NA1];
+          HMX_UNROLL
+          for (int k = 0; k < NA1; ++k) sa[k] = NA > 0 ? s_atoms[(k * T + t) * NRC + ro] : 0.0;
+          // m = M g_a = Mn (e_{pi(a-1)} - e_{pi(a)})
+          double m[D];
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p) {
+            m[p] = 0.0;
+            if (a >= 1) m[p] += Mn[p * D + kuhn_axis<D>(t, a >= 1 ? a - 1 : 0)];
+            if (a < D) m[p] -= Mn[p * D + kuhn_axis<D>(t, a < D ? a : 0)];
+          }
+          double ej[D][NV], sg[D][NV];
+          HMX_UNROLL
+          for (int j = 0; j < D; ++j) {
+            HMX_UNROLL
+            for (int v = 0; v < D; ++v) ej[j][v] = (v == j) ? m[v] : 0.0;
+            int v = D;
+            HMX_UNROLL
+            for (int r = 0; r < D; ++r)
+              HMX_UNROLL
+              for (int cc = r + 1; cc < D; ++cc) {
+                ej[j][v] = ((cc == j) ? m[r] : 0.0) + ((r == j) ? m[cc] : 0.0);
+                ++v;
+              }
+            CO::stress(pc, sa, ej[j], sg[j]);
+          }
+          HMX_UNROLL
+          for (int j = 0; j < D; ++j)
+            HMX_UNROLL
+            for (int j2 = j; j2 < D; ++j2) {
+              double s = 0.0;
+              HMX_UNROLL
+              for (int v = 0; v < NV; ++v) s += sg[j][v] * ej[j2][v];
+              blk[sym_index(D, j, j2)] += vol * s;
+            }
+        }
+      }
+      double inv[NSYM];
+      sym_inverse<D>(blk, inv);
+      HMX_UNROLL
+      for (int k = 0; k < NSYM; ++k) s_dinv[k * N + i] = inv[k];
+    }
+
+    // ---- 3. right-hand sides b_q -> y, r = b, z = Dinv r, p = z ----
+    elasticity_sweep<CO, NM, NT, true>(pc, Mn, s_atoms, s_p, s_y, q, l);  // ends with a barrier
+    double rz[NRHS], rz0[NRHS];
+    bool active[NRHS];
+    {
+      double part = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          double r[D], z[D];
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            r[c] = s_y[(q * D + c) * N + i];
+            s_y[(q * D + c) * N + i] = 0.0;
+            g_r[(q * D + c) * N + i] = r[c];
+            g_x[(q * D + c) * N + i] = 0.0;
+          }
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            z[c] = 0.0;
+            HMX_UNROLL
+            for (int c2 = 0; c2 < D; ++c2) z[c] += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
+            part += r[c] * z[c];
+            s_p[(q * D + c) * N + i] = z[c];
+          }
+        }
+      }
+      part = warp_sum(part);
+      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+      if (lane == 0) buf[warp] = part;
+      sync();
+      HMX_UNROLL
+      for (int qq = 0; qq < NRHS; ++qq) {
+        double s = 0.0;
+        HMX_UNROLL
+        for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
+        rz[qq] = rz0[qq] = s;
+        active[qq] = s > P.atol * P.atol;
+      }
+    }
+    int it = 0;
+    bool any = false;
+    HMX_UNROLL
+    for (int qq = 0; qq < NRHS; ++qq) any = any || active[qq];
+
+    // ---- 4. PCG ----
+    while (any && it < P.max_it) {
+      ++it;
+      elasticity_sweep<CO, NM, NT, false>(pc, Mn, s_atoms, s_p, s_y, q, l);  // y = K p
+      double pAp[NRHS];
+      {
+        double part = 0.0;
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = l + j * TPR;
+          if (i < N) {
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) part += s_p[(q * D + c) * N + i] * s_y[(q * D + c) * N + i];
+          }
+        }
+        part = warp_sum(part);
+        double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+        if (lane == 0) buf[warp] = part;
+        sync();
+        HMX_UNROLL
+        for (int qq = 0; qq < NRHS; ++qq) {
+          double s = 0.0;
+          HMX_UNROLL
+          for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
+          pAp[qq] = s;
+        }
+      }
+      double alpha_all[NRHS];
+      HMX_UNROLL
+      for (int qq = 0; qq < NRHS; ++qq) alpha_all[qq] = (active[qq] && pAp[qq] > 0.0) ? rz[qq] / pAp[qq] : 0.0;
+      double alpha = 0.0;
+      bool mine = false;
+      HMX_UNROLL
+      for (int qq = 0; qq < NRHS; ++qq)
+        if (qq == q) {
+          alpha = alpha_all[qq];
+          mine = active[qq];
+        }
+      {
+        double part = 0.0;
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = l + j * TPR;
+          if (i < N) {
+            double r[D];
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) {
+              const int a = (q * D + c) * N + i;
+              const double yv = s_y[a];
+              s_y[a] = 0.0;
+              r[c] = g_r[a];
+              if (mine) {
+                g_x[a] += alpha * s_p[a];
+                r[c] -= alpha * yv;
+                g_r[a] = r[c];
+              }
+            }
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) {
+              double z = 0.0;
+              HMX_UNROLL
+              for (int c2 = 0; c2 < D; ++c2) z += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
+              part += r[c] * z;
+            }
+          }
+        }
+        part = warp_sum(part);
+        double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+        if (lane == 0) buf[warp] = part;
+        sync();
+        any = false;
+        double beta = 0.0;
+        HMX_UNROLL
+        for (int qq = 0; qq < NRHS; ++qq) {
+          double s = 0.0;
+          HMX_UNROLL
+          for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
+          if (active[qq]) {
+            if (qq == q) beta = s / rz[qq];
+            rz[qq] = s;
+            const double tol = fmax(P.rtol * P.rtol * rz0[qq], P.atol * P.atol);
+            if (!(s > tol)) active[qq] = false;
+          }
+          any = any || active[qq];
+        }
+        if (any) {
+          bool still = false;
+          HMX_UNROLL
+          for (int qq = 0; qq < NRHS; ++qq)
+            if (qq == q) still = active[qq];
+          if (still) {
+            HMX_UNROLL
+            for (int j = 0; j < NPT; ++j) {
+              const int i = l + j * TPR;
+              if (i < N) {
+                double r[D];
+                HMX_UNROLL
+                for (int c = 0; c < D; ++c) r[c] = g_r[(q * D + c) * N + i];
+                HMX_UNROLL
+                for (int c = 0; c < D; ++c) {
+                  double z = 0.0;
+                  HMX_UNROLL
+                  for (int c2 = 0; c2 < D; ++c2) z += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
+                  const int a = (q * D + c) * N + i;
+                  s_p[a] = z + beta * s_p[a];
+                }
+              }
+            }
+          }
+          sync();
+        }
+      }
+    }
+
+    // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
+    sync();  // x and r of every right-hand side are visible to the whole CTA
+    elasticity_sweep<CO, NM, NT, true>(pc, Mn, s_atoms, s_p, s_y, q, l);
+    {
+      double z[2 * NRHS];
+      HMX_UNROLL
+      for (int k = 0; k < 2 * NRHS; ++k) z[k] = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            const double xq = g_x[(q * D + c) * N + i], rq = g_r[(q * D + c) * N + i];
+            HMX_UNROLL
+            for (int p = 0; p < NRHS; ++p) {
+              z[p] += s_y[(p * D + c) * N + i] * xq;           // b_p . x_q
+              z[NRHS + p] += g_x[(p * D + c) * N + i] * rq;    // x_p . r_q
+            }
+          }
+        }
+      }
+      HMX_UNROLL
+      for (int k = 0; k < 2 * NRHS; ++k) z[k] = warp_sum(z[k]);
+      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+      if (lane == 0) {
+        HMX_UNROLL
+        for (int k = 0; k < 2 * NRHS; ++k) buf[warp * L::NREDV + k] = z[k];
+      }
+      sync();
+      if (t_id == 0) {
+        double Ah[NRHS * NRHS];
+        for (int qq = 0; qq < NRHS; ++qq) {
+          double e[NV], sg[NV];
+          HMX_UNROLL
+          for (int v = 0; v < NV; ++v) e[v] = (v == qq) ? 1.0 : 0.0;
+          CO::stress(pc, smean, e, sg);
+          for (int p = 0; p < NRHS; ++p) {
+            double z1 = 0.0, z2 = 0.0;
+            for (int ww = 0; ww < WPR; ++ww) {
+              z1 += buf[(qq * WPR + ww) * L::NREDV + p];
+              z2 += buf[(qq * WPR + ww) * L::NREDV + NRHS + p];
+            }
+            Ah[p * NRHS + qq] = sg[p] - z1 - z2;
+          }
+        }
+        if (P.A_hom != nullptr)
+          for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
+        if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
+        if (P.iters != nullptr) P.iters[pt] = it;
+        if (P.resid != nullptr) {
+          double worst = 0.0;
+          HMX_UNROLL
+          for (int qq = 0; qq < NRHS; ++qq)
+            if (rz0[qq] > P.atol * P.atol) worst = fmax(worst, sqrt(rz[qq] / rz0[qq]));
+          P.resid[pt] = worst;
+        }
+      }
+    }
+    sync();
+    // leave y zeroed for the next macro point (done at the top of the loop)
+  }
+}
+
+}  // namespace hmx

@@ -1,0 +1,57 @@
+// Translation unit of one specialised micro cell kernel.  Compiled once per
+// (coefficient program, micro mesh size, block size) by hommx_b200/native.py:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -cubin
+//        -DHMX_COEFF_FILE="<generated struct HMX_COEFF>" -DHMX_KIND=k -DHMX_NM=n -DHMX_NT=threads
+// The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
+// `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
+#if HMX_KIND == 0
+#include "hmx_cell_poisson.cuh"
+#else
+#include "hmx_cell_elasticity.cuh"
+#endif
+#include HMX_COEFF_FILE
+
+#ifndef HMX_MINB
+#define HMX_MINB 1
+#endif
+
+namespace {
+#if HMX_KIND == 0
+using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+#else
+using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+#endif
+static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
+constexpr int kSmemBytes = Layout::total * 8;
+constexpr int kScratch = Layout::scratch_doubles;
+}  // namespace
+
+#ifndef HMX_EMULATE
+extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
+#if HMX_KIND == 0
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#else
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#endif
+}
+// 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree
+extern "C" __device__ const int hmx_info[8] = {kSmemBytes, HMX_NT,  Layout::NRHS, HMX_COEFF::DIM,
+                                               HMX_KIND,   HMX_NM,  kScratch,     HMX_COEFF::QDEG};
+#else
+#include "emu_runtime.h"
+static void emu_body(void* arg) {
+  const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
+#if HMX_KIND == 0
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#else
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#endif
+}
+extern "C" void hmx_emu_info(int* out) {
+  const int v[8] = {kSmemBytes, HMX_NT, Layout::NRHS, HMX_COEFF::DIM, HMX_KIND, HMX_NM, kScratch, HMX_COEFF::QDEG};
+  for (int i = 0; i < 8; ++i) out[i] = v[i];
+}
+extern "C" void hmx_emu_launch(hmx::CellParams* P, int grid, int host_threads) {
+  hmx::emu::run_grid(grid, HMX_NT, (size_t)Layout::total, emu_body, P, host_threads);
+}
+#endif

@@ -1,0 +1,409 @@
+// Micro cell kernel for the scalar (Poisson) HMM classes: one CTA per macro quadrature point.
+//
+// Replaces, for PoissonHMM / PoissonStratifiedHMM, everything the reference does inside
+// BaseHMM._compute_local_stiffness (hmm.py:334-369): coefficient evaluation, assembly of
+// the periodic micro stiffness matrix (cell_problem.py:367-369), the corrector solves
+// (cell_problem.py:384) and the n_b^2 assemble_scalar passes (hmm.py:361-364), in the
+// equivalent d-RHS / A_hom formulation (hmm.py:1219-1245).
+//
+// Per macro point (all data stays on chip):
+//   1. atoms      : y-dependent scalars of A(x, y) averaged per micro element with the
+//                   quadrature rule handed in by the host (no coefficient array in HBM).
+//   2. operator   : the periodic P1 stiffness matrix has the 7-/15-point stencil of the
+//                   Kuhn mesh; its symmetric half (+ the diagonal) is built in shared
+//                   memory from the atoms and a small per-point table
+//                   kap[k][t][a<b] = |e| g_a^T (M^T C_k M) g_b.
+//   3. PCG        : Jacobi-preconditioned CG in FP64 on all D right-hand sides at once.
+//                   A thread owns NPT nodes: x, r, b live in its registers, only the search
+//                   directions p sit in shared memory; dot products are warp-shuffle +
+//                   one-barrier block reductions.
+//   4. epilogue   : A_hom[p][q] = <A>[p][q] - b_p.x_q - x_p.r_q   (error quadratic in the
+//                   residual), optionally S_loc = |T| G^T A_hom G for the macro cell.
+#pragma once
+#include "hmx_cell_common.cuh"
+
+namespace hmx {
+
+template <class CO, int NM, int NT>
+struct PoissonLayout {
+  static constexpr int D = CO::DIM;
+  static constexpr int T = kuhn_ntypes<D>();
+  static constexpr int N = Grid<D, NM>::N;
+  static constexpr int NRHS = D;
+  static constexpr int NH = (1 << D) - 1;  // stored (positive) stencil directions
+  static constexpr int NW = NT / 32;
+  static constexpr int NA = CO::NATOMS;
+  static constexpr int NA1 = NA > 0 ? NA : 1;
+  static constexpr int NPAIR = D * (D + 1) / 2;
+  static constexpr int NSYM = D * (D + 1) / 2;
+  static constexpr int NRC = AtomIdx<D, NM, CO::YDEP>::NRC;
+  static constexpr int NRED = 2 * NRHS * NRHS > NA1 ? 2 * NRHS * NRHS : NA1;
+  // offsets in doubles
+  static constexpr int o_red = 0;                                    // 2 buffers
+  static constexpr int o_bk = o_red + 2 * NW * NRED;                 // [(1+NA)][NSYM]   M^T C_k M
+  static constexpr int o_rk = o_bk + (1 + NA) * NSYM;                // [(1+NA)][D][D]   M^T C_k
+  static constexpr int o_ck = o_rk + (1 + NA) * D * D;               // [(1+NA)][NSYM]   C_k
+  static constexpr int o_kap = o_ck + (1 + NA) * NSYM;               // [(1+NA)][T][NPAIR]
+  static constexpr int o_beta = o_kap + (1 + NA) * T * NPAIR;        // [NA][T][D+1][NRHS]
+  static constexpr int o_K = ((o_beta + NA1 * T * (D + 1) * NRHS + 1) / 2) * 2;  // [NH][N] half stencil
+  static constexpr int o_p = o_K + NH * N;                           // [NRHS][N] search directions
+  static constexpr int o_atoms = o_p;                                // [NA][T][NRC]: dead once the stencil and
+                                                                     // load vectors exist, so it shares p's storage
+  static constexpr int total = o_p + (NRHS * N > NA1 * T * NRC ? NRHS * N : NA1 * T * NRC);
+  static constexpr int scratch_doubles = 0;
+};
+
+template <class CO, int NM, int NT>
+HMX_DEV void poisson_cell_body(const CellParams& P) {
+  using L = PoissonLayout<CO, NM, NT>;
+  using G = Grid<CO::DIM, NM>;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
+  constexpr int D = L::D, T = L::T, N = L::N, NRHS = L::NRHS, NH = L::NH, NW = L::NW;
+  constexpr int NA = L::NA, NA1 = L::NA1, NPAIR = L::NPAIR, NSYM = L::NSYM, NRC = L::NRC;
+  constexpr int NPT = (N + NT - 1) / NT;
+  constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
+  static_assert(NT % 32 == 0, "block size must be a multiple of the warp size");
+
+  double* sm = dyn_smem();
+  double* s_red = sm + L::o_red;
+  double* s_bk = sm + L::o_bk;
+  double* s_rk = sm + L::o_rk;
+  double* s_ck = sm + L::o_ck;
+  double* s_kap = sm + L::o_kap;
+  double* s_beta = sm + L::o_beta;
+  double* s_atoms = sm + L::o_atoms;
+  double* s_K = sm + L::o_K;
+  double* s_p = sm + L::o_p;
+
+  const int t_id = tid();
+  const double h = 1.0 / (double)NM;
+  const double vol = (D == 2 ? 0.5 : 1.0 / 6.0) * (D == 2 ? h * h : h * h * h);  // |e|
+  int red_flip = 0;
+
+  for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {
+    // ---- 0. macro point, per-point constants, stratification Jacobian (registers) ----
+    double xm[3], verts[(D + 1) * 3];
+    macro_point<D>(P, pt, xm, verts);
+    double pc[NPC1];
+    CO::point_consts(xm, pc);
+    double M[D * D];  // M[p*D+i] = d theta_i / d x_p  (hmm.py:756-757)
+    CO::dtheta(xm, M);
+
+    // ---- 1. atoms: per-element quadrature means on the reduced cube set ----
+    if (NA > 0) {
+      for (int idx = t_id; idx < T * NRC; idx += NT) {
+        const int t = idx / NRC, rc = idx - t * NRC;
+        int c[3];
+        AI::rdecode(rc, c);
+        double acc[NA1];
+        HMX_UNROLL
+        for (int k = 0; k < NA1; ++k) acc[k] = 0.0;
+        for (int q = 0; q < P.nq; ++q) {
+          double y[D], s[NA1];
+          HMX_UNROLL
+          for (int a = 0; a < D; ++a) y[a] = ((double)c[a] + P.qp[(t * P.nq + q) * D + a]) * h;
+          CO::atoms(pc, y, s);
+          const double w = P.qw[q];
+          HMX_UNROLL
+          for (int k = 0; k < NA1; ++k) acc[k] += w * s[k];
+        }
+        HMX_UNROLL
+        for (int k = 0; k < NA; ++k) s_atoms[(k * T + t) * NRC + rc] = acc[k];
+      }
+    }
+    // ---- 2a. C_k (A = C_0 + sum_k s_k C_k), B_k = M^T C_k M, R_k = M^T C_k ----
+    if (t_id <= NA) {
+      double Call[(1 + NA) * NSYM];
+      CO::tensor_affine(pc, Call);
+      double C[D][D];
+      HMX_UNROLL
+      for (int kk = 0; kk <= NA; ++kk)
+        if (kk == t_id) {
+          HMX_UNROLL
+          for (int i = 0; i < D; ++i)
+            HMX_UNROLL
+            for (int j = 0; j < D; ++j) C[i][j] = Call[kk * NSYM + sym_index(D, i, j)];
+        }
+      double R[D][D];  // R[i][q] = sum_p M[p][i] C[p][q]
+      HMX_UNROLL
+      for (int i = 0; i < D; ++i)
+        HMX_UNROLL
+        for (int q = 0; q < D; ++q) {
+          double s = 0.0;
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p) s += M[p * D + i] * C[p][q];
+          R[i][q] = s;
+          s_rk[(t_id * D + i) * D + q] = s;
+        }
+      HMX_UNROLL
+      for (int i = 0; i < D; ++i)
+        HMX_UNROLL
+        for (int j = i; j < D; ++j) {
+          double s = 0.0;
+          HMX_UNROLL
+          for (int q = 0; q < D; ++q) s += R[i][q] * M[q * D + j];
+          s_bk[t_id * NSYM + sym_index(D, i, j)] = s;
+          s_ck[t_id * NSYM + sym_index(D, i, j)] = C[i][j];
+        }
+    }
+    sync();
+    // ---- 2b. element tables: kap (stiffness, pairs a<b) and beta (load vectors) ----
+    {
+      const double w = vol * (double)NM * (double)NM;
+      for (int e = t_id; e < (1 + NA) * T * NPAIR; e += NT) {
+        const int k = e / (T * NPAIR), t = (e / NPAIR) % T, pr = e % NPAIR;
+        int a = 0, b = 1;
+        for (int cnt = 0, aa = 0; aa < D; ++aa)
+          for (int bb = aa + 1; bb <= D; ++bb, ++cnt)
+            if (cnt == pr) {
+              a = aa;
+              b = bb;
+            }
+        // K_e[a][b] = w (B[a-1][b-1] - B[a-1][b] - B[a][b-1] + B[a][b]) in walk order
+        double v = 0.0;
+        for (int da = 0; da < 2; ++da)
+          for (int db = 0; db < 2; ++db) {
+            const int i = a - 1 + da, j = b - 1 + db;
+            if (i < 0 || i >= D || j < 0 || j >= D) continue;
+            const double bij = s_bk[k * NSYM + sym_index(D, kuhn_axis<D>(t, i), kuhn_axis<D>(t, j))];
+            v += (da == db) ? bij : -bij;
+          }
+        s_kap[e] = w * v;
+      }
+      const double wb = -vol * (double)NM;
+      for (int e = t_id; e < NA * T * (D + 1) * NRHS; e += NT) {
+        const int q = e % NRHS, a = (e / NRHS) % (D + 1), t = (e / (NRHS * (D + 1))) % T, k = e / (NRHS * (D + 1) * T);
+        double v = 0.0;
+        if (a >= 1) v += s_rk[((1 + k) * D + kuhn_axis<D>(t, a - 1)) * D + q];
+        if (a < D) v -= s_rk[((1 + k) * D + kuhn_axis<D>(t, a)) * D + q];
+        s_beta[e] = wb * v;
+      }
+    }
+    sync();
+
+    // ---- 2c. half stencil and load vectors of the owned nodes ----
+    double bq[NPT][NRHS];
+    HMX_UNROLL
+    for (int j = 0; j < NPT; ++j) {
+      const int i = t_id + j * NT;
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) bq[j][q] = 0.0;
+      if (i < N) {
+        int c[3];
+        G::decode(i, c);
+        double acc[NH];
+        HMX_UNROLL
+        for (int s = 0; s < NH; ++s) acc[s] = 0.0;
+        HMX_UNROLL
+        for (int t = 0; t < T; ++t) {
+          HMX_UNROLL
+          for (int a = 0; a <= D; ++a) {
+            // node i is vertex a of the type-t element of cube o = c - P(t,a)
+            int o[3];
+            G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
+            const int ro = AI::ridx(o);
+            double sa[NA1];
+            HMX_UNROLL
+            for (int k = 0; k < NA; ++k) sa[k] = s_atoms[(k * T + t) * NRC + ro];
+            HMX_UNROLL
+            for (int k = 0; k < NA; ++k)
+              HMX_UNROLL
+              for (int q = 0; q < NRHS; ++q) bq[j][q] += s_beta[((k * T + t) * (D + 1) + a) * NRHS + q] * sa[k];
+            HMX_UNROLL
+            for (int b = a + 1; b <= D; ++b) {
+              // pair index of (a,b) in the a<b enumeration
+              const int pr = a * D - a * (a - 1) / 2 + (b - a - 1);
+              const int slot = (kuhn_pmask<D>(t, b) & ~kuhn_pmask<D>(t, a)) - 1;
+              double v = s_kap[(0 * T + t) * NPAIR + pr];
+              HMX_UNROLL
+              for (int k = 0; k < NA; ++k) v += s_kap[((1 + k) * T + t) * NPAIR + pr] * sa[k];
+              acc[slot] += v;
+            }
+          }
+        }
+        HMX_UNROLL
+        for (int s = 0; s < NH; ++s) s_K[s * N + i] = acc[s];
+      }
+    }
+    // atom means for <A> (every thread gets them)
+    double smean[NA1];
+    {
+      HMX_UNROLL
+      for (int k = 0; k < NA1; ++k) smean[k] = 0.0;
+      if (NA > 0) {
+        for (int idx = t_id; idx < T * NRC; idx += NT) {
+          HMX_UNROLL
+          for (int k = 0; k < NA; ++k) smean[k] += s_atoms[k * T * NRC + idx];
+        }
+        block_sum<NA1, NW>(smean, s_red + (red_flip ^= 1) * NW * L::NRED);  // also publishes s_K
+        HMX_UNROLL
+        for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * NRC);
+      } else {
+        sync();
+      }
+    }
+    // ---- 2d. diagonal from the zero row sums (constants are in the kernel of K) ----
+    double dinv[NPT], kdiag[NPT];
+    HMX_UNROLL
+    for (int j = 0; j < NPT; ++j) {
+      const int i = t_id + j * NT;
+      dinv[j] = kdiag[j] = 0.0;
+      if (i < N) {
+        int c[3];
+        G::decode(i, c);
+        double d = 0.0;
+        HMX_UNROLL
+        for (int s = 0; s < NH; ++s) d -= s_K[s * N + i] + s_K[s * N + G::template shifted<-1>(c, s + 1)];
+        kdiag[j] = d;
+        dinv[j] = d != 0.0 ? 1.0 / d : 0.0;
+      }
+    }
+
+    // ---- 3. PCG on all right-hand sides ----
+    double xq[NPT][NRHS], rq[NPT][NRHS];
+    double rz[NRHS], rz0[NRHS];
+    bool active[NRHS];
+    {
+      double part[NRHS];
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) part[q] = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = t_id + j * NT;
+        HMX_UNROLL
+        for (int q = 0; q < NRHS; ++q) {
+          xq[j][q] = 0.0;
+          rq[j][q] = bq[j][q];
+          const double z = dinv[j] * rq[j][q];
+          part[q] += rq[j][q] * z;
+          if (i < N) s_p[q * N + i] = z;
+        }
+      }
+      block_sum<NRHS, NW>(part, s_red + (red_flip ^= 1) * NW * L::NRED);  // also publishes p
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) {
+        rz[q] = rz0[q] = part[q];
+        active[q] = part[q] > P.atol * P.atol;
+      }
+    }
+    int it = 0;
+    bool any = false;
+    HMX_UNROLL
+    for (int q = 0; q < NRHS; ++q) any = any || active[q];
+    while (any && it < P.max_it) {
+      ++it;
+      double Ap[NPT][NRHS], pown[NPT][NRHS], pAp[NRHS];
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) pAp[q] = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = t_id + j * NT;
+        HMX_UNROLL
+        for (int q = 0; q < NRHS; ++q) Ap[j][q] = pown[j][q] = 0.0;
+        if (i < N) {
+          int c[3];
+          G::decode(i, c);
+          const double kd = kdiag[j];
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) {
+            pown[j][q] = s_p[q * N + i];
+            Ap[j][q] = kd * pown[j][q];
+          }
+          HMX_UNROLL
+          for (int s = 0; s < NH; ++s) {
+            const int ip = G::template shifted<1>(c, s + 1), im = G::template shifted<-1>(c, s + 1);
+            const double kp = s_K[s * N + i], km = s_K[s * N + im];
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) Ap[j][q] += kp * s_p[q * N + ip] + km * s_p[q * N + im];
+          }
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) pAp[q] += pown[j][q] * Ap[j][q];
+        }
+      }
+      block_sum<NRHS, NW>(pAp, s_red + (red_flip ^= 1) * NW * L::NRED);
+      double alpha[NRHS], part[NRHS];
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) {
+        alpha[q] = (active[q] && pAp[q] > 0.0) ? rz[q] / pAp[q] : 0.0;
+        part[q] = 0.0;
+      }
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j)
+        HMX_UNROLL
+        for (int q = 0; q < NRHS; ++q) {
+          xq[j][q] += alpha[q] * pown[j][q];
+          rq[j][q] -= alpha[q] * Ap[j][q];
+          part[q] += rq[j][q] * rq[j][q] * dinv[j];
+        }
+      block_sum<NRHS, NW>(part, s_red + (red_flip ^= 1) * NW * L::NRED);
+      any = false;
+      double beta[NRHS];
+      HMX_UNROLL
+      for (int q = 0; q < NRHS; ++q) {
+        beta[q] = 0.0;
+        if (active[q]) {
+          beta[q] = part[q] / rz[q];
+          rz[q] = part[q];
+          const double tol = fmax(P.rtol * P.rtol * rz0[q], P.atol * P.atol);
+          if (!(part[q] > tol)) active[q] = false;
+        }
+        any = any || active[q];
+      }
+      if (any) {
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = t_id + j * NT;
+          if (i < N) {
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q)
+              if (active[q]) s_p[q * N + i] = dinv[j] * rq[j][q] + beta[q] * pown[j][q];
+          }
+        }
+        sync();
+      }
+    }
+
+    // ---- 4. epilogue: A_hom = <A> - b_p.x_q - x_p.r_q ----
+    {
+      double z[2 * NRHS * NRHS];
+      HMX_UNROLL
+      for (int k = 0; k < 2 * NRHS * NRHS; ++k) z[k] = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j)
+        HMX_UNROLL
+        for (int p = 0; p < NRHS; ++p)
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) {
+            z[p * NRHS + q] += bq[j][p] * xq[j][q];
+            z[NRHS * NRHS + p * NRHS + q] += xq[j][p] * rq[j][q];
+          }
+      block_sum<2 * NRHS * NRHS, NW>(z, s_red + (red_flip ^= 1) * NW * L::NRED);
+      if (t_id == 0) {
+        double Ah[NRHS * NRHS];
+        HMX_UNROLL
+        for (int p = 0; p < D; ++p)
+          HMX_UNROLL
+          for (int q = 0; q < D; ++q) {
+            double a = s_ck[sym_index(D, p, q)];
+            HMX_UNROLL
+            for (int k = 0; k < NA; ++k) a += s_ck[(1 + k) * NSYM + sym_index(D, p, q)] * smean[k];
+            Ah[p * D + q] = a - z[p * NRHS + q] - z[NRHS * NRHS + p * NRHS + q];
+          }
+        if (P.A_hom != nullptr)
+          for (int k = 0; k < D * D; ++k) P.A_hom[pt * D * D + k] = Ah[k];
+        if (P.S_loc != nullptr) macro_element_matrix<D, 0>(verts, Ah, P.S_loc + pt * (D + 1) * (D + 1));
+        if (P.iters != nullptr) P.iters[pt] = it;
+        if (P.resid != nullptr) {
+          double worst = 0.0;
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q)
+            if (rz0[q] > P.atol * P.atol) worst = fmax(worst, sqrt(rz[q] / rz0[q]));
+          P.resid[pt] = worst;
+        }
+      }
+    }
+    sync();  // shared memory is reused by the next macro point
+  }
+}
+
+}  // namespace hmx

@@ -1,0 +1,561 @@
+// libhmx.so: host side of the C ABI declared in include/hmx.h.
+//
+// The micro cell kernel is compiled per coefficient program (hommx_b200/native.py) and
+// arrives as a cubin image; it is loaded with the driver API, obtained through
+// cudaGetDriverEntryPoint so that the library has no link-time dependency on libcuda.so
+// (it must load -- and export its symbols -- on a machine without a GPU).
+// The macro gather, halo pack/unpack and the peak microbenchmarks are compiled in.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hmx.h"
+#include "hmx_cell_common.cuh"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+// ---- fixed kernels ------------------------------------------------------------------
+// CSR value slot s = sum of its sources in fixed order (deterministic replacement of
+// MatSetValues(ADD_VALUES), hmm.py:325-330).  HBM-bound streaming gather.
+__global__ void __launch_bounds__(256) hmx_gather_csr(long long nnz, const long long* __restrict__ ptr,
+                                                      const int* __restrict__ src, const double* __restrict__ S,
+                                                      double* __restrict__ vals) {
+  for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < nnz; s += (long long)gridDim.x * blockDim.x) {
+    const long long b = ptr[s], e = ptr[s + 1];
+    double acc = 0.0;
+    for (long long j = b; j < e; ++j) acc += S[src[j]];
+    vals[s] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) hmx_halo_pack(long long n, const long long* __restrict__ slots,
+                                                     const double* __restrict__ vals, double* __restrict__ buf) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+    buf[j] = vals[slots[j]];
+}
+__global__ void __launch_bounds__(256) hmx_halo_unpack(long long n, const long long* __restrict__ slots,
+                                                       double* __restrict__ vals, const double* __restrict__ buf) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+    vals[slots[j]] = buf[j];
+}
+// FP64 peak: 8 independent DFMA chains per thread, 1024 threads/SM
+__global__ void __launch_bounds__(256) hmx_dfma_peak(double* out, int iters, double a, double b) {
+  double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      v0 = fma(v0, a, b);
+      v1 = fma(v1, a, b);
+      v2 = fma(v2, a, b);
+      v3 = fma(v3, a, b);
+      v4 = fma(v4, a, b);
+      v5 = fma(v5, a, b);
+      v6 = fma(v6, a, b);
+      v7 = fma(v7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+}
+__global__ void __launch_bounds__(256) hmx_copy(const double2* __restrict__ a, double2* __restrict__ b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    b[i] = a[i];
+}
+
+// ---- driver API entry points ----------------------------------------------------------
+struct Driver {
+  CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+  CUresult (*ModuleUnload)(CUmodule) = nullptr;
+  CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+  CUresult (*ModuleGetGlobal)(CUdeviceptr*, size_t*, CUmodule, const char*) = nullptr;
+  CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+  CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                           void**, void**) = nullptr;
+  CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+template <class F>
+bool load_entry(const char* name, F& fn, std::string& why) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q);
+  if (e != cudaSuccess || p == nullptr) {
+    why = std::string("cudaGetDriverEntryPoint(") + name + "): " + cudaGetErrorString(e);
+    return false;
+  }
+  fn = reinterpret_cast<F>(p);
+  return true;
+}
+
+Driver& driver() {
+  static Driver d;
+  if (!d.ok && d.why.empty()) {
+    d.ok = load_entry("cuModuleLoadData", d.ModuleLoadData, d.why) && load_entry("cuModuleUnload", d.ModuleUnload, d.why) &&
+           load_entry("cuModuleGetFunction", d.ModuleGetFunction, d.why) &&
+           load_entry("cuModuleGetGlobal", d.ModuleGetGlobal, d.why) &&
+           load_entry("cuFuncSetAttribute", d.FuncSetAttribute, d.why) && load_entry("cuLaunchKernel", d.LaunchKernel, d.why) &&
+           load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocksPerMultiprocessor, d.why) &&
+           load_entry("cuGetErrorString", d.GetErrorString, d.why);
+  }
+  return d;
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct hmx_handle {
+  int dim = 0, kind = 0, n_micro = 0, nq = 0, device = 0;
+  double rtol = 1e-8, atol = 1e-10;
+  int max_it = 10000;
+  int info[8] = {0};
+  int grid_override = 0;
+  CUmodule module = nullptr;
+  CUfunction fn = nullptr;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  DevBuf qp, qw, scratch;
+  // staging for the host-pointer entry points
+  DevBuf d_x, d_A, d_it, d_res, d_cells, d_xyz, d_ptr, d_src, d_vals, d_S;
+  mutable std::string err;
+  int ntypes() const { return dim == 2 ? 2 : 6; }
+  int m() const { return kind == HMX_POISSON ? dim : dim * (dim + 1) / 2; }
+  int nb() const { return kind == HMX_POISSON ? dim + 1 : (dim + 1) * dim; }
+};
+
+namespace {
+
+int fail(const hmx_t* h, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h)
+    h->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define HMX_CUDA(h, call)                                                                        \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(h, HMX_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define HMX_CU(h, call)                                                              \
+  do {                                                                               \
+    CUresult r_ = (call);                                                            \
+    if (r_ != CUDA_SUCCESS) {                                                        \
+      const char* s_ = nullptr;                                                      \
+      driver().GetErrorString(r_, &s_);                                              \
+      return fail(h, HMX_ERR_CUDA, "%s: %s", #call, s_ ? s_ : "unknown driver error"); \
+    }                                                                                \
+  } while (0)
+
+int grid_1d(long long n, int threads, int sms) {
+  long long g = (n + threads - 1) / threads;
+  long long cap = (long long)sms * 8;
+  return (int)std::max<long long>(1, std::min(g, cap));
+}
+
+int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_nodes, const double* node_xyz,
+                double* A_hom, double* S_loc, int* iters, double* resid) {
+  if (n_pts == 0) return HMX_OK;
+  const int per_sm = std::max(1, h->info[5]);
+  const int sms = h->info[6];
+  long long grid = (long long)per_sm * sms;
+  if (h->grid_override > 0) grid = h->grid_override;
+  grid = std::max<long long>(1, std::min<long long>(grid, n_pts));
+  const size_t scratch_doubles = (size_t)h->info[7] * (size_t)grid;
+  if (scratch_doubles) HMX_CUDA(h, h->scratch.reserve(scratch_doubles * sizeof(double)));
+  hmx::CellParams P;
+  P.n_pts = n_pts;
+  P.x_pts = x_pts;
+  P.cell_nodes = cell_nodes;
+  P.node_xyz = node_xyz;
+  P.A_hom = A_hom;
+  P.S_loc = S_loc;
+  P.iters = iters;
+  P.resid = resid;
+  P.qp = h->qp.as<double>();
+  P.qw = h->qw.as<double>();
+  P.scratch = h->scratch.as<double>();
+  P.nq = h->nq;
+  P.max_it = h->max_it;
+  P.rtol = h->rtol;
+  P.atol = h->atol;
+  void* args[] = {&P};
+  HMX_CU(h, driver().LaunchKernel(h->fn, (unsigned)grid, 1, 1, (unsigned)h->info[1], 1, 1, (unsigned)h->info[0],
+                                  (CUstream)h->stream, args, nullptr));
+  return HMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hmx_last_error(const hmx_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int hmx_create(hmx_t** out, const hmx_desc* d) {
+  if (!out || !d) return fail(nullptr, HMX_ERR_ARG, "hmx_create: null argument");
+  *out = nullptr;
+  if (d->dim != 2 && d->dim != 3) return fail(nullptr, HMX_ERR_ARG, "Topology should be 3D or 2D");  // hmm.py:104-105
+  if (d->kind != HMX_POISSON && d->kind != HMX_ELASTICITY) return fail(nullptr, HMX_ERR_ARG, "unknown problem kind %d", d->kind);
+  if (d->n_micro < 2) return fail(nullptr, HMX_ERR_ARG, "the periodic micro mesh needs at least 2 cells per axis");
+  if (d->nq < 1 || !d->qp || !d->qw) return fail(nullptr, HMX_ERR_ARG, "quadrature table missing");
+  if (!d->kernel_image || d->kernel_image_size == 0)
+    return fail(nullptr, HMX_ERR_KERNEL, "no cell kernel image: the CUDA path has no fallback");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, HMX_ERR_CUDA, "no CUDA device available (the hot path has no CPU fallback)");
+  }
+  if (d->device < 0 || d->device >= ndev) return fail(nullptr, HMX_ERR_ARG, "device %d out of range (%d devices)", d->device, ndev);
+  HMX_CUDA(nullptr, cudaSetDevice(d->device));
+  HMX_CUDA(nullptr, cudaFree(nullptr));  // make the primary context current for the driver API
+  Driver& drv = driver();
+  if (!drv.ok) return fail(nullptr, HMX_ERR_CUDA, "%s", drv.why.c_str());
+
+  hmx_t* h = new hmx_t;
+  h->dim = d->dim;
+  h->kind = d->kind;
+  h->n_micro = d->n_micro;
+  h->nq = d->nq;
+  h->device = d->device;
+  h->rtol = d->rtol;
+  h->atol = d->atol;
+  h->max_it = d->max_it > 0 ? d->max_it : 10000;
+  auto bail = [&](int code) {
+    g_create_error = h->err;
+    hmx_destroy(h);
+    return code;
+  };
+  {
+    CUresult r = drv.ModuleLoadData(&h->module, d->kernel_image);
+    if (r != CUDA_SUCCESS) {
+      const char* s = nullptr;
+      drv.GetErrorString(r, &s);
+      fail(h, HMX_ERR_KERNEL, "cuModuleLoadData: %s (image not built for this GPU?)", s ? s : "?");
+      return bail(HMX_ERR_KERNEL);
+    }
+    r = drv.ModuleGetFunction(&h->fn, h->module, "hmx_cell");
+    if (r != CUDA_SUCCESS) {
+      fail(h, HMX_ERR_KERNEL, "kernel image has no entry 'hmx_cell'");
+      return bail(HMX_ERR_KERNEL);
+    }
+    CUdeviceptr gp = 0;
+    size_t gs = 0;
+    r = drv.ModuleGetGlobal(&gp, &gs, h->module, "hmx_info");
+    if (r != CUDA_SUCCESS || gs < 8 * sizeof(int)) {
+      fail(h, HMX_ERR_KERNEL, "kernel image has no 'hmx_info' table");
+      return bail(HMX_ERR_KERNEL);
+    }
+    int ki[8];
+    if (cudaMemcpy(ki, (const void*)gp, sizeof ki, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      fail(h, HMX_ERR_CUDA, "reading hmx_info failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return bail(HMX_ERR_CUDA);
+    }
+    // ki: 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 reserved
+    if (ki[3] != d->dim || ki[4] != d->kind || ki[5] != d->n_micro) {
+      fail(h, HMX_ERR_KERNEL, "kernel image was built for dim=%d kind=%d n=%d, descriptor says dim=%d kind=%d n=%d", ki[3], ki[4],
+           ki[5], d->dim, d->kind, d->n_micro);
+      return bail(HMX_ERR_KERNEL);
+    }
+    h->info[0] = ki[0];
+    h->info[1] = ki[1];
+    h->info[2] = ki[2];
+    h->info[3] = h->m();
+    h->info[4] = h->nb();
+    h->info[7] = ki[6];
+    r = drv.FuncSetAttribute(h->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, ki[0]);
+    if (r != CUDA_SUCCESS) {
+      fail(h, HMX_ERR_KERNEL, "cell kernel needs %d bytes of shared memory per CTA: not available on this device", ki[0]);
+      return bail(HMX_ERR_KERNEL);
+    }
+    int per_sm = 0;
+    r = drv.OccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, h->fn, ki[1], (size_t)ki[0]);
+    if (r != CUDA_SUCCESS || per_sm < 1) {
+      fail(h, HMX_ERR_KERNEL, "cell kernel cannot be resident on an SM (threads=%d smem=%d)", ki[1], ki[0]);
+      return bail(HMX_ERR_KERNEL);
+    }
+    h->info[5] = per_sm;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) {
+      fail(h, HMX_ERR_CUDA, "cudaGetDeviceProperties failed");
+      return bail(HMX_ERR_CUDA);
+    }
+    h->info[6] = prop.multiProcessorCount;
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fail(h, HMX_ERR_CUDA, "cudaStreamCreate failed");
+    return bail(HMX_ERR_CUDA);
+  }
+  h->own_stream = true;
+  const size_t nqp = (size_t)h->ntypes() * d->nq * d->dim;
+  if (h->qp.reserve(nqp * sizeof(double)) != cudaSuccess || h->qw.reserve(d->nq * sizeof(double)) != cudaSuccess ||
+      cudaMemcpy(h->qp.p, d->qp, nqp * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(h->qw.p, d->qw, d->nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+    fail(h, HMX_ERR_CUDA, "uploading the quadrature table failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return bail(HMX_ERR_CUDA);
+  }
+  *out = h;
+  return HMX_OK;
+}
+
+void hmx_destroy(hmx_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
+                    &h->d_src, &h->d_vals, &h->d_S})
+    b->release();
+  if (h->module && driver().ok) driver().ModuleUnload(h->module);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int hmx_set_stream(hmx_t* h, void* s) {
+  if (!h) return HMX_ERR_ARG;
+  if (h->own_stream && h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return HMX_OK;
+}
+
+int hmx_set_tolerances(hmx_t* h, double rtol, double atol, int32_t max_it) {
+  if (!h) return HMX_ERR_ARG;
+  if (rtol < 0 || atol < 0 || max_it < 0) return fail(h, HMX_ERR_ARG, "tolerances must be non-negative");
+  h->rtol = rtol;
+  h->atol = atol;
+  if (max_it > 0) h->max_it = max_it;
+  return HMX_OK;
+}
+
+int hmx_set_grid(hmx_t* h, int32_t n) {
+  if (!h || n < 0) return HMX_ERR_ARG;
+  h->grid_override = n;
+  return HMX_OK;
+}
+
+int hmx_kernel_info(const hmx_t* h, int32_t info[8]) {
+  if (!h || !info) return HMX_ERR_ARG;
+  for (int i = 0; i < 8; ++i) info[i] = h->info[i];
+  return HMX_OK;
+}
+
+int hmx_sync(hmx_t* h) {
+  if (!h) return HMX_ERR_ARG;
+  HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HMX_OK;
+}
+
+int hmx_cell_tensors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_pts < 0 || (n_pts > 0 && (!x_pts || !A_hom))) return fail(h, HMX_ERR_ARG, "hmx_cell_tensors: null buffer");
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  return launch_cell(h, n_pts, x_pts, nullptr, nullptr, A_hom, nullptr, iters, resid);
+}
+
+int hmx_cell_tensors(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_pts < 0 || (n_pts > 0 && (!x_pts || !A_hom))) return fail(h, HMX_ERR_ARG, "hmx_cell_tensors: null buffer");
+  if (n_pts == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  const size_t mm = (size_t)h->m() * h->m();
+  HMX_CUDA(h, h->d_x.reserve(n_pts * 3 * sizeof(double)));
+  HMX_CUDA(h, h->d_A.reserve(n_pts * mm * sizeof(double)));
+  HMX_CUDA(h, h->d_it.reserve(n_pts * sizeof(int)));
+  HMX_CUDA(h, h->d_res.reserve(n_pts * sizeof(double)));
+  HMX_CUDA(h, cudaMemcpyAsync(h->d_x.p, x_pts, n_pts * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  int rc = launch_cell(h, n_pts, h->d_x.as<double>(), nullptr, nullptr, h->d_A.as<double>(), nullptr, h->d_it.as<int>(),
+                       h->d_res.as<double>());
+  if (rc != HMX_OK) return rc;
+  HMX_CUDA(h, cudaMemcpyAsync(A_hom, h->d_A.p, n_pts * mm * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (iters) HMX_CUDA(h, cudaMemcpyAsync(iters, h->d_it.p, n_pts * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (resid) HMX_CUDA(h, cudaMemcpyAsync(resid, h->d_res.p, n_pts * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HMX_OK;
+}
+
+int hmx_assemble_macro_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int64_t n_nodes, const double* node_xyz,
+                           int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src, double* csr_vals, double* S_loc,
+                           int32_t* iters, double* resid) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_cells < 0 || nnz < 0 || n_nodes < 0) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: negative size");
+  if (n_cells > 0 && (!cell_nodes || !node_xyz)) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null mesh buffer");
+  if (nnz > 0 && (!gather_ptr || !csr_vals || (n_cells > 0 && !gather_src)))
+    return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null CSR buffer");
+  const size_t nb2 = (size_t)h->nb() * h->nb();
+  if ((double)n_cells * (double)nb2 > 2147483647.0)
+    return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: n_cells*n_b^2 exceeds the int32 range of gather_src; shard the cells");
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  double* S = S_loc;
+  if (!S && n_cells > 0) {
+    HMX_CUDA(h, h->d_S.reserve(n_cells * nb2 * sizeof(double)));
+    S = h->d_S.as<double>();
+  }
+  int rc = launch_cell(h, n_cells, nullptr, cell_nodes, node_xyz, nullptr, S, iters, resid);
+  if (rc != HMX_OK) return rc;
+  if (nnz > 0) {
+    const int g = grid_1d(nnz, 256, h->info[6]);
+    hmx_gather_csr<<<g, 256, 0, h->stream>>>(nnz, (const long long*)gather_ptr, gather_src, S, csr_vals);
+    HMX_CUDA(h, cudaGetLastError());
+  }
+  return HMX_OK;
+}
+
+int hmx_assemble_macro(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int64_t n_nodes, const double* node_xyz, int64_t nnz,
+                       const int64_t* gather_ptr, const int32_t* gather_src, double* csr_vals, double* S_loc, int32_t* iters,
+                       double* resid) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_cells < 0 || nnz < 0 || n_nodes < 0) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: negative size");
+  if (n_cells > 0 && (!cell_nodes || !node_xyz)) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null mesh buffer");
+  if (nnz > 0 && (!gather_ptr || !csr_vals)) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null CSR buffer");
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  const int nv = h->dim + 1;
+  const size_t nb2 = (size_t)h->nb() * h->nb();
+  std::vector<int64_t> last(1, 0);
+  int64_t nsrc = 0;
+  if (nnz > 0) nsrc = gather_ptr[nnz];
+  if (nsrc < 0 || (double)nsrc > (double)n_cells * (double)nb2)
+    return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: gather_ptr[nnz]=%lld exceeds n_cells*n_b^2", (long long)nsrc);
+  if (nsrc > 0 && !gather_src) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null gather_src");
+  HMX_CUDA(h, h->d_cells.reserve(std::max<size_t>(1, n_cells * nv * sizeof(int))));
+  HMX_CUDA(h, h->d_xyz.reserve(std::max<size_t>(1, n_nodes * 3 * sizeof(double))));
+  HMX_CUDA(h, h->d_ptr.reserve((nnz + 1) * sizeof(int64_t)));
+  HMX_CUDA(h, h->d_src.reserve(std::max<size_t>(1, nsrc * sizeof(int))));
+  HMX_CUDA(h, h->d_vals.reserve(std::max<size_t>(1, nnz * sizeof(double))));
+  HMX_CUDA(h, h->d_S.reserve(std::max<size_t>(1, n_cells * nb2 * sizeof(double))));
+  HMX_CUDA(h, h->d_it.reserve(std::max<size_t>(1, n_cells * sizeof(int))));
+  HMX_CUDA(h, h->d_res.reserve(std::max<size_t>(1, n_cells * sizeof(double))));
+  if (n_cells > 0) {
+    HMX_CUDA(h, cudaMemcpyAsync(h->d_cells.p, cell_nodes, n_cells * nv * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    HMX_CUDA(h, cudaMemcpyAsync(h->d_xyz.p, node_xyz, n_nodes * 3 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  if (nnz > 0) {
+    HMX_CUDA(h, cudaMemcpyAsync(h->d_ptr.p, gather_ptr, (nnz + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    if (nsrc > 0) HMX_CUDA(h, cudaMemcpyAsync(h->d_src.p, gather_src, nsrc * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = hmx_assemble_macro_dev(h, n_cells, h->d_cells.as<int>(), n_nodes, h->d_xyz.as<double>(), nnz, h->d_ptr.as<int64_t>(),
+                                  h->d_src.as<int>(), h->d_vals.as<double>(), h->d_S.as<double>(), h->d_it.as<int>(),
+                                  h->d_res.as<double>());
+  if (rc != HMX_OK) return rc;
+  if (nnz > 0) HMX_CUDA(h, cudaMemcpyAsync(csr_vals, h->d_vals.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (n_cells > 0) {
+    if (S_loc) HMX_CUDA(h, cudaMemcpyAsync(S_loc, h->d_S.p, n_cells * nb2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (iters) HMX_CUDA(h, cudaMemcpyAsync(iters, h->d_it.p, n_cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (resid) HMX_CUDA(h, cudaMemcpyAsync(resid, h->d_res.p, n_cells * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HMX_OK;
+}
+
+int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, int64_t n, double* buf) {
+  if (!h) return HMX_ERR_ARG;
+  if (n < 0 || (n > 0 && (!csr_vals || !slots || !buf))) return fail(h, HMX_ERR_ARG, "hmx_halo_pack: null buffer");
+  if (n == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  hmx_halo_pack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
+  HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_t n, const double* buf) {
+  if (!h) return HMX_ERR_ARG;
+  if (n < 0 || (n > 0 && (!csr_vals || !slots || !buf))) return fail(h, HMX_ERR_ARG, "hmx_halo_unpack: null buffer");
+  if (n == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
+  HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+int hmx_measure_peaks(int32_t device, double* fp64_tflops, double* copy_gbs) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(nullptr, HMX_ERR_CUDA, "no CUDA device %d", device);
+  }
+  HMX_CUDA(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HMX_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t e0, e1;
+  HMX_CUDA(nullptr, cudaEventCreate(&e0));
+  HMX_CUDA(nullptr, cudaEventCreate(&e1));
+  if (fp64_tflops) {
+    const int blocks = prop.multiProcessorCount * 4, threads = 256, iters = 4096;
+    double* out = nullptr;
+    HMX_CUDA(nullptr, cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaEventRecord(e0);
+      hmx_dfma_peak<<<blocks, threads>>>(out, iters, 1.0000001, 1e-9);
+      cudaEventRecord(e1);
+      HMX_CUDA(nullptr, cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0) best = std::min(best, ms);
+    }
+    cudaFree(out);
+    const double flops = 2.0 * 64.0 * iters * (double)blocks * threads;
+    *fp64_tflops = flops / (best * 1e-3) / 1e12;
+  }
+  if (copy_gbs) {
+    const long long n = 1LL << 26;  // 64 Mi double2 = 1 GiB per buffer
+    double2 *a = nullptr, *b = nullptr;
+    HMX_CUDA(nullptr, cudaMalloc(&a, n * sizeof(double2)));
+    HMX_CUDA(nullptr, cudaMalloc(&b, n * sizeof(double2)));
+    cudaMemset(a, 0, n * sizeof(double2));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+      cudaEventRecord(e0);
+      hmx_copy<<<prop.multiProcessorCount * 16, 256>>>(a, b, n);
+      cudaEventRecord(e1);
+      HMX_CUDA(nullptr, cudaEventSynchronize(e1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (rep > 0) best = std::min(best, ms);
+    }
+    cudaFree(a);
+    cudaFree(b);
+    *copy_gbs = 2.0 * n * sizeof(double2) / (best * 1e-3) / 1e9;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return HMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+"""ctypes binding of libhmx.so (include/hmx.h) and the build of the coefficient-specialised
+cell kernels.
+
+The reference JIT-compiles ``1 + n_b + n_b^2`` FFCx forms per assembly
+(/root/reference/src/hommx/hmm.py:259-274, 306).  Here one CUDA kernel is compiled per
+(coefficient program, micro mesh size) with ``nvcc`` for sm_100a into a cubin that is cached
+in-tree (``hommx_b200/_kcache``) and handed to ``hmx_create`` as an image.  There is no CPU
+fallback: if the library or a CUDA device is missing every compute call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import shutil
+import subprocess
+import threading
+
+import numpy as np
+
+from .codegen import ELASTICITY, POISSON, CoefficientProgram
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+KCACHE = os.path.join(_HERE, "_kcache")
+LIB_PATH = os.path.join(_HERE, "libhmx.so")
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+_HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh", "hmx_cell_entry.cu")
+
+
+class HmxError(RuntimeError):
+    pass
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise HmxError("nvcc not found: the cell kernels cannot be built (there is no CPU fallback)")
+    return exe
+
+
+# ----------------------------------------------------------------------------
+# libhmx.so
+# ----------------------------------------------------------------------------
+def build_library(force=False, verbose=False):
+    """Compile hommx_b200/csrc/hmx_lib.cu into hommx_b200/libhmx.so (in-tree, so that it
+    travels to the GPU box)."""
+    src = os.path.join(CSRC, "hmx_lib.cu")
+    deps = [src, os.path.join(INCLUDE, "hmx.h")] + [os.path.join(CSRC, h) for h in _HEADERS[:2]]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+           "-o", LIB_PATH, src]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise HmxError(f"building libhmx.so failed:\n{r.stderr}")
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+class hmx_desc(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("kind", C.c_int32), ("n_micro", C.c_int32), ("nq", C.c_int32),
+        ("qp", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double)),
+        ("kernel_image", C.c_void_p), ("kernel_image_size", C.c_size_t),
+        ("rtol", C.c_double), ("atol", C.c_double), ("max_it", C.c_int32), ("device", C.c_int32),
+    ]  # fmt: skip
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+# name -> (restype, argtypes); every symbol include/hmx.h declares
+SYMBOLS = {
+    "hmx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(hmx_desc)]),
+    "hmx_destroy": (None, [C.c_void_p]),
+    "hmx_last_error": (C.c_char_p, [C.c_void_p]),
+    "hmx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmx_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_int32]),
+    "hmx_set_grid": (C.c_int, [C.c_void_p, C.c_int32]),
+    "hmx_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "hmx_cell_tensors": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_cell_tensors_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_assemble_macro": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_assemble_macro_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_measure_peaks": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "hmx_sync": (C.c_int, [C.c_void_p]),
+}  # fmt: skip
+
+
+def load_library():
+    """dlopen hommx_b200/libhmx.so (building it first if the sources are newer)."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                build_library()
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SYMBOLS.items():
+                fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+# ----------------------------------------------------------------------------
+# cell kernels
+# ----------------------------------------------------------------------------
+def default_threads(dim, kind, n):
+    """Threads per CTA for the cell kernel of an n^dim micro mesh."""
+    N = n**dim
+    if kind == POISSON:
+        nt = -(-N // 2)  # two nodes per thread
+        nt = max(64, min(1024, 32 * (-(-nt // 32))))
+        return nt
+    nrhs = dim * (dim + 1) // 2
+    ncol = 2**dim
+    per = -(-N // ncol)  # cubes of one colour (even n)
+    tpr = max(32, min(64, 32 * (-(-per // 32))))
+    return tpr * nrhs
+
+
+def _src_hash():
+    hsh = hashlib.sha1()
+    for name in _HEADERS:
+        p = os.path.join(CSRC, name)
+        if os.path.exists(p):
+            with open(p, "rb") as f:
+                hsh.update(f.read())
+    return hsh.hexdigest()[:12]
+
+
+def kernel_key(prog: CoefficientProgram, n, threads):
+    return f"{'p' if prog.kind == POISSON else 'e'}{prog.dim}_n{n}_t{threads}_{prog.key}_{_src_hash()}"
+
+
+def kernel_defines(prog, n, threads, coeff_path):
+    return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}"]
+
+
+def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_log=True):
+    """nvcc -cubin of the cell kernel for this coefficient program; returns the cubin path."""
+    threads = threads or default_threads(prog.dim, prog.kind, n)
+    os.makedirs(KCACHE, exist_ok=True)
+    key = kernel_key(prog, n, threads)
+    cubin = os.path.join(KCACHE, key + ".cubin")
+    if os.path.exists(cubin) and not force:
+        return cubin
+    coeff = os.path.join(KCACHE, key + ".coeff.cuh")
+    with open(coeff, "w") as f:
+        f.write(prog.source)
+    tmp = cubin + f".tmp{os.getpid()}"
+    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I", CSRC,
+           *kernel_defines(prog, n, threads, coeff), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
+    if keep_log:
+        with open(os.path.join(KCACHE, key + ".ptxas.log"), "w") as f:
+            f.write(" ".join(cmd) + "\n" + r.stderr)
+    os.replace(tmp, cubin)
+    return cubin
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class CellSolver:
+    """One ``hmx_t`` handle: a (problem class, coefficient, micro mesh, quadrature) combination.
+
+    ``qp`` has shape (T, nq, dim) (cube-local quadrature points per element type, in units of
+    h) and ``qw`` (nq,) normalised weights -- built by ``hommx_b200.micro.quadrature_table``.
+    """
+
+    def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None):
+        self.prog = prog
+        self.dim, self.kind, self.n = prog.dim, prog.kind, int(n_micro)
+        self.m = prog.n_rhs
+        self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
+        self._h = C.c_void_p()
+        self.lib = load_library()
+        cubin = compile_kernel(prog, self.n, threads)
+        with open(cubin, "rb") as f:
+            image = f.read()
+        self._image = C.create_string_buffer(image, len(image))
+        qp = np.ascontiguousarray(qp, dtype=np.float64)
+        qw = np.ascontiguousarray(qw, dtype=np.float64)
+        T = 2 if self.dim == 2 else 6
+        if qp.shape != (T, len(qw), self.dim):
+            raise ValueError(f"quadrature points must have shape {(T, len(qw), self.dim)}, got {qp.shape}")
+        d = hmx_desc(self.dim, self.kind, self.n, len(qw), qp.ctypes.data_as(C.POINTER(C.c_double)),
+                     qw.ctypes.data_as(C.POINTER(C.c_double)), C.cast(self._image, C.c_void_p), len(image),
+                     rtol, atol, max_it, device)  # fmt: skip
+        rc = self.lib.hmx_create(C.byref(self._h), C.byref(d))
+        if rc != 0:
+            msg = self.lib.hmx_last_error(None).decode()
+            self._h = C.c_void_p()
+            if rc == -1:
+                raise ValueError(msg)
+            raise HmxError(f"hmx_create failed ({rc}): {msg}")
+        info = (C.c_int32 * 8)()
+        self._check(self.lib.hmx_kernel_info(self._h, info))
+        self.info = dict(zip(("smem_bytes", "threads", "n_rhs", "m", "n_b", "ctas_per_sm", "sms", "scratch_doubles"), info))
+
+    # -- plumbing ----------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.hmx_last_error(self._h).decode()
+            if rc == -1:
+                raise ValueError(msg)
+            raise HmxError(f"libhmx error {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.hmx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.hmx_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+
+    def set_tolerances(self, rtol, atol, max_it=0):
+        self._check(self.lib.hmx_set_tolerances(self._h, rtol, atol, max_it))
+
+    def set_grid(self, n_ctas):
+        self._check(self.lib.hmx_set_grid(self._h, int(n_ctas)))
+
+    def sync(self):
+        self._check(self.lib.hmx_sync(self._h))
+
+    # -- host-buffer entry points ------------------------------------------------------
+    def cell_tensors(self, x_pts, return_stats=False):
+        x = np.ascontiguousarray(np.asarray(x_pts, dtype=np.float64).reshape(-1, 3))
+        n = len(x)
+        A = np.empty((n, self.m, self.m))
+        it = np.empty(n, dtype=np.int32)
+        res = np.empty(n)
+        self._check(self.lib.hmx_cell_tensors(self._h, n, _ptr(x), _ptr(A), _ptr(it), _ptr(res)))
+        return (A, it, res) if return_stats else A
+
+    def assemble_macro(self, cell_nodes, node_xyz, gather_ptr, gather_src, want_local=False, return_stats=False):
+        cells = np.ascontiguousarray(cell_nodes, dtype=np.int32).reshape(-1, self.dim + 1)
+        xyz = np.ascontiguousarray(node_xyz, dtype=np.float64).reshape(-1, 3)
+        gp = np.ascontiguousarray(gather_ptr, dtype=np.int64)
+        gs = np.ascontiguousarray(gather_src, dtype=np.int32)
+        nnz = len(gp) - 1
+        nc = len(cells)
+        vals = np.empty(nnz)
+        S = np.empty((nc, self.nb, self.nb)) if want_local else None
+        it = np.empty(nc, dtype=np.int32)
+        res = np.empty(nc)
+        self._check(self.lib.hmx_assemble_macro(self._h, nc, _ptr(cells), len(xyz), _ptr(xyz), nnz, _ptr(gp), _ptr(gs),
+                                                _ptr(vals), _ptr(S), _ptr(it), _ptr(res)))  # fmt: skip
+        out = (vals,)
+        if want_local:
+            out += (S,)
+        if return_stats:
+            out += (it, res)
+        return out if len(out) > 1 else vals
+
+    # -- device-pointer entry points (torch tensors or raw addresses) -----------------------
+    @staticmethod
+    def _dp(t):
+        if t is None:
+            return None
+        return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+
+    def cell_tensors_dev(self, n_pts, x_pts, A_hom, iters=None, resid=None):
+        dp = self._dp
+        self._check(self.lib.hmx_cell_tensors_dev(self._h, int(n_pts), dp(x_pts), dp(A_hom), dp(iters), dp(resid)))
+
+    def assemble_macro_dev(self, n_cells, cell_nodes, n_nodes, node_xyz, nnz, gather_ptr, gather_src, csr_vals, S_loc=None,
+                           iters=None, resid=None):
+        dp = self._dp
+        self._check(self.lib.hmx_assemble_macro_dev(self._h, int(n_cells), dp(cell_nodes), int(n_nodes), dp(node_xyz), int(nnz),
+                                                    dp(gather_ptr), dp(gather_src), dp(csr_vals), dp(S_loc), dp(iters),
+                                                    dp(resid)))  # fmt: skip
+
+    def halo_pack_dev(self, csr_vals, slots, n, buf):
+        dp = self._dp
+        self._check(self.lib.hmx_halo_pack_dev(self._h, dp(csr_vals), dp(slots), int(n), dp(buf)))
+
+    def halo_unpack_dev(self, csr_vals, slots, n, buf):
+        dp = self._dp
+        self._check(self.lib.hmx_halo_unpack_dev(self._h, dp(csr_vals), dp(slots), int(n), dp(buf)))
+
+
+def measure_peaks(device=0):
+    """(FP64 DFMA TFLOP/s, device copy GB/s) measured on `device` by libhmx's microbenchmarks."""
+    lib = load_library()
+    f, c = C.c_double(), C.c_double()
+    rc = lib.hmx_measure_peaks(device, C.byref(f), C.byref(c))
+    if rc != 0:
+        raise HmxError(lib.hmx_last_error(None).decode())
+    return f.value, c.value

@@ -1,0 +1,116 @@
+/* hmx.h -- C ABI of libhmx.so, the B200 (sm_100a) replacement for the hot path of
+ * flxrcz/hommx: the per-macro-quadrature-point periodic micro cell problems and the
+ * macro stiffness assembly they feed.
+ *
+ * The reference has no FFI for this path: the seam is the Python method
+ * BaseHMM._assemble_stiffness (src/hommx/hmm.py:298-332), which loops over macro cells,
+ * calls _compute_local_stiffness (hmm.py:334-369) and MatSetValues(ADD_VALUES)
+ * (hmm.py:325-330).  The entry points below are what a binding for that seam binds;
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to hmm.py.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on
+ * success or a negative hmx_status; the message is available from hmx_last_error().  A
+ * handle is not thread-safe; it owns one CUDA stream (replaceable with hmx_set_stream) and
+ * its device buffers; the caller owns every buffer it passes in.  Functions ending in _dev
+ * take device pointers and only enqueue work on the handle's stream (no synchronisation);
+ * the others take host pointers, copy in and out on that stream and return after
+ * synchronising it.  There is no CPU fallback: without a CUDA device every compute entry
+ * point fails with HMX_ERR_CUDA.
+ */
+#ifndef HMX_H
+#define HMX_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hmx_handle hmx_t;
+
+enum hmx_status {
+  HMX_OK = 0,
+  HMX_ERR_ARG = -1,     /* invalid argument (the reference raises ValueError, hmm.py:104-115) */
+  HMX_ERR_CUDA = -2,    /* CUDA runtime/driver failure, or no device */
+  HMX_ERR_KERNEL = -3,  /* cell kernel image missing/incompatible with the descriptor */
+  HMX_ERR_STATE = -4,   /* call sequence error (e.g. assemble before hmx_macro_plan) */
+  HMX_ERR_NOMEM = -5
+};
+
+enum hmx_kind { HMX_POISSON = 0, HMX_ELASTICITY = 1 };
+
+/* Describes one solver object = one (problem class, coefficient, micro mesh) combination;
+ * replaces BaseHMM._setup_cell_problem_variables / _setup_cell_problem_forms
+ * (hmm.py:178-207, 259-274). */
+typedef struct hmx_desc {
+  int32_t dim;       /* 2 or 3 (micro and macro dimension agree, hmm.py:114-115) */
+  int32_t kind;      /* hmx_kind */
+  int32_t n_micro;   /* cells per axis of the structured periodic micro mesh */
+  int32_t nq;        /* quadrature points per micro element */
+  const double* qp;  /* [T][nq][dim] points per element type, cube-local, units of h (T = dim!) */
+  const double* qw;  /* [nq] weights, normalised to sum 1 */
+  const void* kernel_image; /* cubin/fatbin of the cell kernel specialised for the coefficient */
+  size_t kernel_image_size;
+  double rtol;       /* PCG: stop at sqrt(r.z) <= max(rtol*sqrt(r0.z0), atol) (ksp_rtol / ksp_atol) */
+  double atol;
+  int32_t max_it;    /* ksp_max_it */
+  int32_t device;    /* CUDA device ordinal */
+} hmx_desc;
+
+int hmx_create(hmx_t** out, const hmx_desc* desc);
+void hmx_destroy(hmx_t* h);
+/* message of the last failure on `h`; with h == NULL the last hmx_create failure */
+const char* hmx_last_error(const hmx_t* h);
+
+/* use an existing CUDA stream (cudaStream_t) for all work of this handle */
+int hmx_set_stream(hmx_t* h, void* cuda_stream);
+int hmx_set_tolerances(hmx_t* h, double rtol, double atol, int32_t max_it);
+/* 0 = one resident wave of CTAs (default), otherwise the grid size to launch */
+int hmx_set_grid(hmx_t* h, int32_t n_ctas);
+
+/* static facts about the loaded kernel: info[0]=dynamic smem bytes, [1]=threads per CTA,
+ * [2]=right-hand sides per point, [3]=m (A_hom is m x m), [4]=n_b (S_loc is n_b x n_b),
+ * [5]=CTAs per SM, [6]=SM count, [7]=per-CTA scratch doubles */
+int hmx_kernel_info(const hmx_t* h, int32_t info[8]);
+
+/* Homogenised tensors at given macro points: replaces the n_b corrector solves and n_b^2
+ * assemble_scalar calls of _compute_local_stiffness (hmm.py:354-364) in the d-RHS form of
+ * BasePeriodicHMM.compute_effective_tensor (hmm.py:1219-1245).
+ *   x_pts [n_pts][3], A_hom [n_pts][m][m], iters [n_pts] (may be NULL), resid [n_pts] (may be NULL) */
+int hmx_cell_tensors(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid);
+int hmx_cell_tensors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid);
+
+/* Macro stiffness assembly: replaces BaseHMM._assemble_stiffness (hmm.py:298-332) for the
+ * `n_cells` macro cells given (a rank's owned cells, hmm.py:307).
+ *   cell_nodes [n_cells][dim+1]  macro vertex ids (geometry dofmap)
+ *   node_xyz   [n_nodes][3]      macro vertex coordinates (msh.geometry.x)
+ *   gather_ptr [nnz+1], gather_src [gather_ptr[nnz]]: for CSR value slot s the sources
+ *       S_loc_flat[gather_src[j]], j in [gather_ptr[s], gather_ptr[s+1]), S_loc_flat being
+ *       the [n_cells][n_b][n_b] row-major local matrices (row = unrolled dof i, hmm.py:31-40,
+ *       325-330).  The fixed order makes the sum deterministic.
+ *   csr_vals   [nnz]  out: summed values (un-BC'd, what self._A holds before hmm.py:442)
+ *   S_loc      [n_cells][n_b*n_b] out, may be NULL;  iters/resid [n_cells], may be NULL */
+int hmx_assemble_macro(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int64_t n_nodes, const double* node_xyz,
+                       int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src, double* csr_vals,
+                       double* S_loc, int32_t* iters, double* resid);
+int hmx_assemble_macro_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int64_t n_nodes,
+                           const double* node_xyz, int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src,
+                           double* csr_vals, double* S_loc, int32_t* iters, double* resid);
+
+/* Halo exchange helpers for macro cells sharded over several GPUs (the one exchange step of
+ * the reference: MatAssembly of shared rows, hmm.py:442).  pack: buf[j] = csr_vals[slots[j]];
+ * the caller sums `buf` across ranks (torch.distributed / NCCL all-reduce); unpack writes it
+ * back.  All pointers are device pointers. */
+int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, int64_t n, double* buf);
+int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_t n, const double* buf);
+
+/* Roofline denominators measured on this device: FP64 FMA throughput (register-resident DFMA
+ * chains on every SM) in TFLOP/s and a device-to-device copy in GB/s (read+write bytes). */
+int hmx_measure_peaks(int32_t device, double* fp64_tflops, double* copy_gbs);
+
+int hmx_sync(hmx_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMX_H */

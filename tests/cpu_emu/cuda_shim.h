@@ -1,0 +1,66 @@
+// CPU emulation of the few CUDA facilities the hommx_b200 cell kernels use.
+// TEST INFRASTRUCTURE ONLY: lets `pytest -m "not gpu"` run the unmodified kernel source
+// (hommx_b200/csrc/*.cuh) on the host and compare it with the oracle before GPU time is
+// spent.  Nothing under hommx_b200/ includes or links this file.
+//
+// Every CUDA thread of a CTA is a ucontext fiber; fibers run round-robin, each up to its
+// next barrier / warp collective, which reproduces __syncthreads() semantics exactly for
+// kernels whose threads all execute the same sequence of barriers (true for ours).
+#pragma once
+#include <math.h>
+#include <stddef.h>
+
+#define HMX_DEV inline
+#define HMX_HOSTDEV inline
+#define HMX_RESTRICT __restrict__
+#define HMX_UNROLL
+#define __device__
+#define __forceinline__ inline
+#define HMX_GLOBAL(maxthreads, minblocks) void
+
+namespace hmx {
+namespace emu {
+struct Cta {
+  int nthreads, bid, nblocks, cur;
+  double* smem;
+  double* wbuf;  // [2][nthreads] warp collective exchange
+  int* wpar;     // [nthreads] per-fiber parity
+};
+extern thread_local Cta* g_cta;
+void yield();  // return to the scheduler until every fiber has arrived
+}  // namespace emu
+
+inline int tid() { return emu::g_cta->cur; }
+inline int bid() { return emu::g_cta->bid; }
+inline int nblocks() { return emu::g_cta->nblocks; }
+inline void sync() { emu::yield(); }
+inline double* dyn_smem() { return emu::g_cta->smem; }
+inline double warp_sum(double v) {
+  emu::Cta* c = emu::g_cta;
+  const int me = c->cur, par = c->wpar[me];
+  c->wbuf[par * c->nthreads + me] = v;
+  c->wpar[me] = par ^ 1;
+  emu::yield();
+  const int w0 = (me / 32) * 32;
+  // same association as the xor butterfly of the device code
+  double t[32];
+  for (int l = 0; l < 32; ++l) t[l] = c->wbuf[par * c->nthreads + w0 + l];
+  for (int m = 16; m > 0; m >>= 1) {
+    double u[32];
+    for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ m];
+    for (int l = 0; l < 32; ++l) t[l] = u[l];
+  }
+  return t[me & 31];
+}
+inline double warp_max(double v) {
+  emu::Cta* c = emu::g_cta;
+  const int me = c->cur, par = c->wpar[me];
+  c->wbuf[par * c->nthreads + me] = v;
+  c->wpar[me] = par ^ 1;
+  emu::yield();
+  const int w0 = (me / 32) * 32;
+  double m = c->wbuf[par * c->nthreads + w0];
+  for (int l = 1; l < 32; ++l) m = fmax(m, c->wbuf[par * c->nthreads + w0 + l]);
+  return m;
+}
+}  // namespace hmx

@@ -1,0 +1,94 @@
+// Fiber scheduler behind cuda_shim.h (TEST INFRASTRUCTURE ONLY).
+#pragma once
+#include <ucontext.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "cuda_shim.h"
+
+namespace hmx {
+namespace emu {
+thread_local Cta* g_cta = nullptr;
+
+struct Sched {
+  ucontext_t main_ctx;
+  std::vector<ucontext_t> ctx;
+  std::vector<char> done;
+  std::vector<char*> stacks;
+  void (*body)(void*);
+  void* arg;
+};
+thread_local Sched* g_sched = nullptr;
+
+void yield() {
+  Sched* s = g_sched;
+  swapcontext(&s->ctx[g_cta->cur], &s->main_ctx);
+}
+
+static void fiber_entry() {
+  Sched* s = g_sched;
+  s->body(s->arg);
+  s->done[g_cta->cur] = 1;
+  swapcontext(&s->ctx[g_cta->cur], &s->main_ctx);
+}
+
+// run one CTA: nthreads fibers over `body`
+inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, void (*body)(void*), void* arg) {
+  constexpr size_t STACK = 256 * 1024;
+  Cta cta;
+  cta.nthreads = nthreads;
+  cta.bid = bid;
+  cta.nblocks = nblocks;
+  cta.cur = 0;
+  std::vector<double> smem(smem_doubles + 2, 0.0), wbuf(2 * nthreads, 0.0);
+  std::vector<int> wpar(nthreads, 0);
+  cta.smem = smem.data();
+  cta.wbuf = wbuf.data();
+  cta.wpar = wpar.data();
+  Sched s;
+  s.body = body;
+  s.arg = arg;
+  s.ctx.resize(nthreads);
+  s.done.assign(nthreads, 0);
+  s.stacks.resize(nthreads);
+  g_cta = &cta;
+  g_sched = &s;
+  for (int t = 0; t < nthreads; ++t) {
+    s.stacks[t] = (char*)std::malloc(STACK);
+    getcontext(&s.ctx[t]);
+    s.ctx[t].uc_stack.ss_sp = s.stacks[t];
+    s.ctx[t].uc_stack.ss_size = STACK;
+    s.ctx[t].uc_link = &s.main_ctx;
+    makecontext(&s.ctx[t], fiber_entry, 0);
+  }
+  bool alive = true;
+  while (alive) {
+    alive = false;
+    for (int t = 0; t < nthreads; ++t) {
+      if (s.done[t]) continue;
+      cta.cur = t;
+      swapcontext(&s.main_ctx, &s.ctx[t]);
+      if (!s.done[t]) alive = true;
+    }
+  }
+  for (int t = 0; t < nthreads; ++t) std::free(s.stacks[t]);
+  g_cta = nullptr;
+  g_sched = nullptr;
+}
+
+// run a grid, CTAs spread over host threads
+inline void run_grid(int grid, int nthreads, size_t smem_doubles, void (*body)(void*), void* arg, int host_threads) {
+  if (host_threads < 1) host_threads = 1;
+  if (host_threads > grid) host_threads = grid;
+  std::vector<std::thread> pool;
+  for (int w = 0; w < host_threads; ++w)
+    pool.emplace_back([=]() {
+      for (int b = w; b < grid; b += host_threads) run_cta(nthreads, b, grid, smem_doubles, body, arg);
+    });
+  for (auto& th : pool) th.join();
+}
+}  // namespace emu
+}  // namespace hmx

@@ -1,0 +1,46 @@
+"""The unmodified CUDA kernel source, compiled by g++ against tests/cpu_emu (fibers for CUDA
+threads), compared with the oracle.  Checks the kernel LOGIC without a GPU; the same cases run
+on the real device in tests/test_gpu_parity.py."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cpu_emu"))
+import cases as K  # noqa: E402
+import emu  # noqa: E402
+from oracle import hmm_oracle as ho  # noqa: E402
+
+LIGHT = [c for c in K.CASES if not c.heavy]
+
+
+@pytest.mark.parametrize("case", LIGHT, ids=[c.name for c in LIGHT])
+def test_cell_tensor_matches_oracle(case):
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, threads=case.threads)
+    x = K.points(case, 2)
+    Ah, it, res = s.cell_tensors(x, return_stats=True)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max(), (case.name, it, res)
+
+
+@pytest.mark.parametrize("name", ["p2_fulltensor_strat_n9", "p3_fulltensor_shear_n5", "e2_hooke_sin_strat_n7", "e3_hooke_smooth_n4"])
+def test_local_matrix_matches_oracle(name):
+    """Fused mode: macro cell vertices in, S_loc out (hmm.py:334-369 end to end)."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, threads=case.threads)
+    cells, xyz = K.random_simplices(case.dim, 2)
+    S, Ah = s.local_matrices(cells, xyz)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(cells)):
+        verts = xyz[cells[k]]
+        Ao = K.oracle_tensor(case, mic, verts.mean(axis=0))
+        So = ho.local_stiffness_from_tensor(Ao, verts, mic.kind)
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+        assert np.abs(S[k] - So).max() <= case.tol * np.abs(So).max()
