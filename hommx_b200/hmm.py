@@ -1,0 +1,336 @@
+"""Drop-in HMM solver classes on the B200 hot path.
+
+Same constructor arguments and ``solve()`` / ``set_boundary_conditions()`` /
+``set_right_hand_side()`` / ``function_space`` surface as the reference's
+``PoissonHMM``, ``PoissonStratifiedHMM``, ``LinearElasticityHMM`` and
+``LinearElasticityStratifiedHMM`` (/root/reference/src/hommx/hmm.py:514-1067).  What changes is
+``_assemble_stiffness`` (hmm.py:298-332): instead of a Python loop over macro cells with ``n_b``
+PETSc solves and ``n_b^2`` ``assemble_scalar`` calls per cell, the owned cells go to the GPU in
+one call (``hmx_assemble_macro``): coefficient evaluation, micro solves, A_hom, S_loc and the
+deterministic gather into the CSR value array all happen on the device.  When macro cells are
+sharded over several GPUs (``torch.distributed`` initialised, one process per GPU) the only
+collective is the sum of the value slots shared between ranks.
+
+Host code stays Python.  DOLFINx / PETSc are not installable in the build image, so the mesh,
+function-space and Dirichlet objects are the light stand-ins of ``hommx_b200.mesh`` /
+``hommx_b200.fem`` (a ``dolfinx.mesh.Mesh`` is accepted wherever its ``geometry`` /
+``topology`` attributes suffice), coefficients are traced with ``hommx_b200.ufl`` (UFL's
+operator names), and the macro linear solve -- outside the hot path, PETSc KSP in the
+reference (hmm.py:482-483) -- is done with scipy.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from . import assembly, codegen, fem, micro, native, quadrature
+from .mesh import as_simplex_mesh
+
+_CELL_OPTION_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it"}
+
+
+def _triangle_area(points):
+    """hmm.py:20-23"""
+    p = np.asarray(points, dtype=float)
+    return 0.5 * np.linalg.norm(np.cross(p[1] - p[0], p[2] - p[0]))
+
+
+def _tetrahedron_volume(points):
+    """hmm.py:25-28"""
+    p = np.asarray(points, dtype=float)
+    return abs(np.linalg.det(np.array([p[1] - p[0], p[2] - p[0], p[3] - p[0]]))) / 6.0
+
+
+class BaseHMM:
+    """Common driver (mirrors ``BaseHMM``, hmm.py:53-511)."""
+
+    _KIND = codegen.POISSON
+
+    def __init__(
+        self,
+        msh,
+        A,
+        f,
+        msh_micro,
+        eps,
+        petsc_options_global_solve=None,
+        petsc_options_cell_problem=None,
+        petsc_options_prefix="hommx_HMM",
+        *,
+        Dtheta_transpose=None,
+        quadrature_rule=None,
+        device=None,
+    ):
+        self._logger = logging.getLogger(__name__)
+        self._msh = as_simplex_mesh(msh)
+        self._cell_mesh = as_simplex_mesh(msh_micro)
+        self._coeff = A
+        self._f = f
+        self._eps = eps
+        self._tdim = self._msh.dim
+        # same checks, same messages as hmm.py:104-115
+        if self._tdim not in (2, 3):
+            raise ValueError("Topology should be 3D or 2D")
+        if self._tdim == 2 and np.any(self._msh.x[:, 2] != 0.0):
+            raise ValueError(
+                "Topological dimension is different from geometrical dimension. Currently surfaces in 3D are not supported."
+            )
+        if self._cell_mesh.dim == 2 and np.any(self._cell_mesh.x[:, 2] != 0.0):
+            raise ValueError("Topological dimension is different from geometrical dimension for micro mesh.")
+        if self._tdim != self._cell_mesh.dim:
+            raise ValueError("Micro and macro mesh should have the same dimensionality.")
+        self._volume_function = _tetrahedron_volume if self._tdim == 3 else _triangle_area
+
+        self._bs = 1 if self._KIND == codegen.POISSON else self._tdim
+        self._V_macro = fem.FunctionSpace(self._msh, self._bs)
+        self._macro_coordinates = self._V_macro.tabulate_dof_coordinates()
+        self._num_basis_functions_per_cell = (self._tdim + 1) * self._bs
+        self._num_global_dofs = self._V_macro.num_dofs
+        self._u = fem.Function(self._V_macro)
+        self._b = np.zeros(self._num_global_dofs)
+        self._needs_reassembly = True
+        self._bcs = []
+
+        if petsc_options_cell_problem is None:
+            petsc_options_cell_problem = {"ksp_atol": 1e-10}  # hmm.py:153-155
+        self._petsc_options_cell_problem = dict(petsc_options_cell_problem)
+        ignored = sorted(set(self._petsc_options_cell_problem) - _CELL_OPTION_KEYS)
+        if ignored:
+            self._logger.warning(
+                "cell problems are solved by the CUDA PCG kernel; PETSc options %s have no meaning there and are ignored", ignored
+            )
+        # PETSc's default rtol (1e-5, left in force by the reference) bounds the residual of GMRES+ILU;
+        # the PCG kernel stops on the energy-norm residual, for which 1e-8 gives A_hom to ~1e-12.
+        self._cell_rtol = float(self._petsc_options_cell_problem.get("ksp_rtol", 1e-8))
+        self._cell_atol = float(self._petsc_options_cell_problem.get("ksp_atol", 1e-10))
+        self._cell_max_it = int(self._petsc_options_cell_problem.get("ksp_max_it", 10000))
+        self._petsc_options_global_solve = dict(petsc_options_global_solve or {})
+        self._petsc_options_prefix = petsc_options_prefix
+
+        # ---- _setup_cell_problem_variables (hmm.py:178-207) ----
+        self._structure = micro.detect_structure(self._cell_mesh)
+        self._program = codegen.build_program(A, self._tdim, self._KIND, Dtheta_transpose)
+        pts, wts = quadrature_rule if quadrature_rule is not None else quadrature.default_rule(self._tdim, self._program.degree)
+        self._qp, self._qw = micro.quadrature_table(self._structure, pts, wts)
+        self._cell_mesh_area = 1.0  # |Y| of the unit box (hmm.py:101)
+
+        # ---- macro sparsity and slot map (replaces the un-preallocated AIJ of hmm.py:144-149) ----
+        self._pattern = assembly.build_pattern(self._msh.cells, self._msh.num_nodes, self._bs)
+        self._A_values = np.zeros(self._pattern.nnz)
+        self._A = None
+        self._device = device
+        self._solver = None
+        self._dev = None
+        self._rank, self._world = 0, 1
+        self.cell_iterations = None
+        self.cell_residuals = None
+
+    # ------------------------------------------------------------------ API surface
+    @property
+    def function_space(self):
+        """Function space of the macro mesh (hmm.py:173-176)."""
+        return self._V_macro
+
+    def set_boundary_conditions(self, bcs):
+        """hmm.py:276-287"""
+        self._bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
+        self._needs_reassembly = True
+
+    def set_right_hand_side(self, f):
+        """hmm.py:289-296"""
+        self._f = f
+
+    # ------------------------------------------------------------------ device plumbing
+    def _ensure_solver(self):
+        if self._solver is not None:
+            return
+        import torch
+        import torch.distributed as dist
+
+        if not torch.cuda.is_available():
+            raise native.HmxError("no CUDA device: the HMM hot path runs on the GPU only (there is no CPU fallback)")
+        if dist.is_available() and dist.is_initialized():
+            self._rank, self._world = dist.get_rank(), dist.get_world_size()
+        dev = self._device
+        if dev is None:
+            dev = torch.cuda.current_device()
+        self._device = int(dev)
+        self._solver = native.CellSolver(
+            self._program, self._structure.n, self._qp, self._qw, rtol=self._cell_rtol, atol=self._cell_atol,
+            max_it=self._cell_max_it, device=self._device,
+        )  # fmt: skip
+        tdev = torch.device("cuda", self._device)
+        n_cells = self._msh.num_cells
+        lo, hi = assembly.shard_range(n_cells, self._rank, self._world)
+        gm = assembly.build_gather(self._pattern.slot_map[lo:hi], self._pattern.nnz)
+        d = {
+            "lo": lo, "hi": hi,
+            "cells": torch.as_tensor(np.ascontiguousarray(self._msh.cells[lo:hi], dtype=np.int32), device=tdev),
+            "xyz": torch.as_tensor(self._msh.x, device=tdev),
+            "ptr": torch.as_tensor(gm.ptr, device=tdev),
+            "src": torch.as_tensor(gm.src, device=tdev),
+            "vals": torch.zeros(self._pattern.nnz, dtype=torch.float64, device=tdev),
+            "S": torch.zeros((hi - lo, self._num_basis_functions_per_cell**2), dtype=torch.float64, device=tdev),
+            "it": torch.zeros(hi - lo, dtype=torch.int32, device=tdev),
+            "res": torch.zeros(hi - lo, dtype=torch.float64, device=tdev),
+        }  # fmt: skip
+        if self._world > 1:
+            sh = assembly.shared_slots(self._pattern.slot_map, n_cells, self._world, self._pattern.nnz)
+            d["shared"] = torch.as_tensor(sh, device=tdev)
+            d["halo"] = torch.zeros(len(sh), dtype=torch.float64, device=tdev)
+        self._dev = d
+
+    # ------------------------------------------------------------------ hot path
+    def _assemble_stiffness(self):
+        """GPU replacement of hmm.py:298-332 (+ the exchange of hmm.py:442 when sharded)."""
+        if not self._needs_reassembly:
+            return
+        import torch
+
+        self._ensure_solver()
+        d = self._dev
+        with torch.cuda.device(self._device):
+            self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+            self._solver.assemble_macro_dev(
+                d["hi"] - d["lo"], d["cells"], self._msh.num_nodes, d["xyz"], self._pattern.nnz, d["ptr"], d["src"], d["vals"],
+                d["S"], d["it"], d["res"],
+            )  # fmt: skip
+            if self._world > 1:
+                self._halo_sum()
+            self.cell_iterations = d["it"].cpu().numpy()
+            self.cell_residuals = d["res"].cpu().numpy()
+            S = d["S"]
+            if bool(torch.isnan(S).any()):
+                bad = torch.nonzero(torch.isnan(S).any(dim=1)).flatten().cpu().numpy() + d["lo"]
+                for c in bad[:10]:  # hmm.py:320-323: logged, not raised
+                    self._logger.error(f"Something went wrong when calculating local matrix on cell {c}")
+            worst = self.cell_iterations.max(initial=0)
+            if worst >= self._cell_max_it:  # hmm.py:427-430
+                self._logger.error(f"Cell problem PCG hit ksp_max_it={self._cell_max_it} on {(self.cell_iterations >= self._cell_max_it).sum()} cells")
+            self._A_values = self._full_values()
+        self._A = sp.csr_matrix((self._A_values, self._pattern.indices, self._pattern.indptr), shape=(self._num_global_dofs,) * 2)
+        self._needs_reassembly = False
+
+    def _halo_sum(self):
+        """Sum of the value slots shared between ranks: the only collective of the path."""
+        import torch.distributed as dist
+
+        d = self._dev
+        n = d["shared"].numel()
+        if n == 0:
+            return
+        self._solver.halo_pack_dev(d["vals"], d["shared"], n, d["halo"])
+        dist.all_reduce(d["halo"], op=dist.ReduceOp.SUM)
+        self._solver.halo_unpack_dev(d["vals"], d["shared"], n, d["halo"])
+
+    def _full_values(self):
+        """Complete CSR values on every rank for the (host, scipy) macro solve; outside the hot path.
+        After the halo sum shared slots are complete everywhere and all other slots live on one rank."""
+        import torch
+        import torch.distributed as dist
+
+        d = self._dev
+        if self._world == 1:
+            return d["vals"].cpu().numpy()
+        v = d["vals"].clone()
+        if self._rank != 0:
+            v[d["shared"]] = 0.0
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        return v.cpu().numpy()
+
+    def _compute_local_stiffness(self, local_cell_index):
+        """One macro cell (the finer seam, hmm.py:334-369): returns the (n_b, n_b) local matrix."""
+        self._ensure_solver()
+        nb = self._num_basis_functions_per_cell
+        cells = np.ascontiguousarray(self._msh.cells[local_cell_index : local_cell_index + 1], dtype=np.int32)
+        gp = np.arange(nb * nb + 1, dtype=np.int64)
+        gs = np.arange(nb * nb, dtype=np.int32)
+        _, S = self._solver.assemble_macro(cells, self._msh.x, gp, gs, want_local=True)
+        return S[0]
+
+    def cell_tensors(self, points):
+        """Homogenised tensors A_hom at arbitrary macro points, shape (n, m, m)."""
+        self._ensure_solver()
+        return self._solver.cell_tensors(points)
+
+    # ------------------------------------------------------------------ solve (hmm.py:434-491)
+    def solve(self):
+        self._assemble_stiffness()
+        A = self._A.copy().tocsr()
+        b = fem.assemble_load(self._V_macro, self._f)
+        for bc in self._bcs:  # Dirichlet lifting, one condition at a time as in hmm.py:453-480
+            u_bc = np.zeros(self._num_global_dofs)
+            u_bc[bc.dofs] = bc.values
+            b = b - A @ u_bc
+            keep = np.ones(self._num_global_dofs)
+            keep[bc.dofs] = 0.0
+            Dk = sp.diags(keep)
+            A = (Dk @ A @ Dk + sp.diags(1.0 - keep)).tocsr()
+            b[bc.dofs] = bc.values
+        self._b = b
+        # macro solve: PETSc KSP in the reference (hmm.py:482-483); a direct scipy solve here
+        x = spla.spsolve(A.tocsc(), b)
+        if not np.all(np.isfinite(x)):  # hmm.py:485-488: logged, not raised
+            self._logger.error("Something went wrong in the global problem solve.")
+        self._u.x.array[:] = x
+        return self._u
+
+    def plot_solution(self, u=None):
+        """hmm.py:493-511 (needs pyvista, as in the reference)."""
+        import pyvista as pv  # noqa: F401
+
+        raise NotImplementedError("plotting is outside the hot path; use the mesh and u.x.array with pyvista directly")
+
+
+# ----------------------------------------------------------------------------------------------
+class PoissonHMM(BaseHMM):
+    """-div(A(x, x/eps) grad u) = f with zero Dirichlet data on the bounding box by default
+    (hmm.py:514-667)."""
+
+    _KIND = codegen.POISSON
+
+    def __init__(self, msh, A, f, msh_micro, eps, petsc_options_global_solve=None, petsc_options_cell_problem=None,
+                 petsc_options_prefix="hommx_PoissonHMM", **kw):  # fmt: skip
+        super().__init__(msh, A, f, msh_micro, eps, petsc_options_global_solve, petsc_options_cell_problem,
+                         petsc_options_prefix, **kw)  # fmt: skip
+        dofs = fem.boundary_nodes(self._msh)  # hmm.py:598-636
+        self._bcs = [fem.dirichletbc(0.0, dofs, self._V_macro)]
+
+
+class PoissonStratifiedHMM(BaseHMM):
+    """Stratified micro structure A(x, theta(x)/eps); ``Dtheta_transpose(x)[p][i] = d theta_i / d x_p``
+    (hmm.py:670-789).  No default boundary condition, as in the reference."""
+
+    _KIND = codegen.POISSON
+
+    def __init__(self, msh, A, f, msh_micro, eps, Dtheta_transpose, petsc_options_global_solve=None,
+                 petsc_options_cell_problem=None, petsc_options_prefix="hommx_PoissonStratifiedHMM", **kw):  # fmt: skip
+        super().__init__(msh, A, f, msh_micro, eps, petsc_options_global_solve, petsc_options_cell_problem,
+                         petsc_options_prefix, Dtheta_transpose=Dtheta_transpose, **kw)  # fmt: skip
+
+
+class LinearElasticityHMM(BaseHMM):
+    """-div(A(x, x/eps) : e(u)) = f, A a rank-4 tensor; no default boundary condition (hmm.py:792-922)."""
+
+    _KIND = codegen.ELASTICITY
+
+    def __init__(self, msh, A, f, msh_micro, eps, petsc_options_global_solve=None, petsc_options_cell_problem=None,
+                 petsc_options_prefix="hommx_LinearElasticityHMM", **kw):  # fmt: skip
+        super().__init__(msh, A, f, msh_micro, eps, petsc_options_global_solve, petsc_options_cell_problem,
+                         petsc_options_prefix, **kw)  # fmt: skip
+
+
+class LinearElasticityStratifiedHMM(BaseHMM):
+    """Stratified linear elasticity (hmm.py:925-1067; the reference's default prefix repeats
+    "hommx_LinearElasticityHMM", hmm.py:986 -- kept)."""
+
+    _KIND = codegen.ELASTICITY
+
+    def __init__(self, msh, A, f, msh_micro, eps, Dtheta_transpose, petsc_options_global_solve=None,
+                 petsc_options_cell_problem=None, petsc_options_prefix="hommx_LinearElasticityHMM", **kw):  # fmt: skip
+        super().__init__(msh, A, f, msh_micro, eps, petsc_options_global_solve, petsc_options_cell_problem,
+                         petsc_options_prefix, Dtheta_transpose=Dtheta_transpose, **kw)  # fmt: skip

@@ -37,6 +37,9 @@ CASES = [
     Case("p2_analytic1_n15", 2, 0, 15, "analytic1"),
     Case("p2_analytic2_n15", 2, 0, 15, "analytic2"),
     Case("p2_periodic_n8", 2, 0, 8, "periodic_only"),
+    Case("p2_smooth_n8", 2, 0, 8, "smooth_sin"),
+    Case("p2_laminate_wavy_n8", 2, 0, 8, "laminate", "dtheta_wavy"),
+    Case("p3_smooth_n4", 3, 0, 4, "smooth_sin"),
     Case("p2_xonly_n7", 2, 0, 7, "x_only"),
     Case("p2_laminate_wavy_n16", 2, 0, 16, "laminate", "dtheta_wavy"),
     Case("p2_laminate_wavy_n32_c2", 2, 0, 32, "laminate", "dtheta_wavy"),  # BASELINE config 2

@@ -1,0 +1,146 @@
+"""End-to-end parity of the drop-in classes on the GPU: assembled macro matrix and macro solution
+against the oracle (the literal restatement of hmm.py:298-369 + :434-491) on identical meshes, and
+the known answers the reference's own tests pin."""
+import math
+
+import numpy as np
+import pytest
+
+import coefficients as Cf
+from hommx_b200 import (
+    LinearElasticityHMM,
+    LinearElasticityStratifiedHMM,
+    PoissonHMM,
+    PoissonStratifiedHMM,
+    fem,
+    mesh,
+)
+from hommx_b200 import ufl as pufl
+from oracle import hmm_oracle as ho
+from oracle import meshes as omesh
+from oracle import npufl
+
+pytestmark = pytest.mark.gpu
+TIGHT = {"ksp_rtol": 1e-10, "ksp_atol": 1e-12}
+
+
+def _np_dtheta(name):
+    Dt = getattr(Cf, name)(npufl)
+    return lambda x: np.asarray(Dt(np.asarray(x, float)))[..., 0]
+
+
+def test_poisson_hmm_matrix_and_solution_match_oracle():
+    """BASELINE config 1 scaled down: PoissonHMM, A = 1.1 + x0 + sin(2 pi y0) (examples/hmm.py:15-16)."""
+    nm, n = 6, 8
+    s = PoissonHMM(mesh.create_unit_square(nm, nm), Cf.smooth_sin(pufl), lambda x: 1.0, mesh.create_unit_square(n, n), 2.0**-5,
+                   petsc_options_cell_problem=TIGHT)  # fmt: skip
+    u = s.solve()
+    macro = omesh.create_unit_square(nm, nm)
+    mic = ho.MicroCell(omesh.create_unit_square(n, n), "poisson", 3)
+    Ao = ho.assemble_macro(macro, mic, Cf.smooth_sin(npufl), 2.0**-5, literal=True)
+    assert np.linalg.norm((s._A - Ao).toarray()) <= 1e-10 * np.linalg.norm(Ao.toarray())
+    bc = ho.boundary_nodes(macro)
+    uo = ho.solve_dirichlet(Ao, ho.assemble_rhs(macro, lambda x: 1.0 + 0 * x[0], 1, degree=1), bc, np.zeros(len(bc)))
+    assert np.abs(u.x.array - uo).max() <= 1e-8 * np.abs(uo).max()
+    # the finer seam: one local matrix
+    S = s._compute_local_stiffness(5)
+    So = ho.local_stiffness_literal(mic, Cf.smooth_sin(npufl), macro.x[macro.cells[5]], 2.0**-5)
+    assert np.abs(S - So).max() <= 1e-10 * np.abs(So).max()
+
+
+def test_poisson_stratified_matches_oracle_and_closed_form():
+    """BASELINE config 2 scaled down: wavy laminate (examples/diffusion/laminate.py:101-117)."""
+    nm, n = 5, 8
+    m = mesh.create_unit_square(nm, nm)
+    s = PoissonStratifiedHMM(m, Cf.laminate(pufl), lambda x: 1.0, mesh.create_unit_square(n, n), 1e-5, Cf.dtheta_wavy(pufl),
+                             petsc_options_cell_problem=TIGHT)  # fmt: skip
+    V = s.function_space
+    left = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[0], 0.0))
+    right = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[0], 1.0))
+    s.set_boundary_conditions([fem.dirichletbc(1.0, left, V), fem.dirichletbc(0.0, right, V)])  # laminate.py:62-86
+    u = s.solve()
+    macro = omesh.create_unit_square(nm, nm)
+    mic = ho.MicroCell(omesh.create_unit_square(n, n), "poisson", 0)
+    Ao = ho.assemble_macro(macro, mic, Cf.laminate(npufl), 1e-5, _np_dtheta("dtheta_wavy"))
+    assert np.linalg.norm((s._A - Ao).toarray()) <= 1e-10 * np.linalg.norm(Ao.toarray())
+    b = ho.assemble_rhs(macro, lambda x: 1.0 + 0 * x[0], 1, degree=1)
+    dofs = np.concatenate([left, right])
+    uo = ho.solve_dirichlet(Ao, b, dofs, np.concatenate([np.ones(len(left)), np.zeros(len(right))]))
+    assert np.abs(u.x.array - uo).max() <= 1e-8 * np.abs(uo).max()
+    # closed form: <a>(I - n n^T) + <1/a>^-1 n n^T with n = M e0 / |M e0|
+    x = np.array([[0.3, 0.6, 0.0]])
+    Ah = s.cell_tensors(x)[0]
+    M = _np_dtheta("dtheta_wavy")(x[0])
+    nv = M[:, 0] / np.linalg.norm(M[:, 0])
+    expect = 2.525 * (np.eye(2) - np.outer(nv, nv)) + (1.0 / (0.5 / 5 + 0.5 / 0.05)) * np.outer(nv, nv)
+    assert np.allclose(Ah, expect, rtol=1e-10, atol=1e-12)
+
+
+def test_reference_analytic_example_1():
+    """test/integration/test_integration_poisson.py:121-143: squared L2 error < 5e-5 on 15x15 / 15x15,
+    and the discrete A_hom values of SURVEY 8c.1."""
+
+    def f(x):
+        return pufl.pi**2 * (1 / 2 + 1 / pufl.sqrt(3)) * pufl.sin(pufl.pi * x[0]) * pufl.sin(pufl.pi * x[1])
+
+    s = PoissonHMM(mesh.create_unit_square(15, 15), Cf.analytic1(pufl), f, mesh.create_unit_square(15, 15), 0.1 / 15,
+                   petsc_options_cell_problem={"ksp_atol": 1e-10})  # fmt: skip
+    u = s.solve()
+    err = ho.l2_error_squared(omesh.create_unit_square(15, 15), u.x.array, lambda x: np.sin(np.pi * x[0]) * np.sin(np.pi * x[1]))
+    assert err < 5e-5
+    Ah = s.cell_tensors(np.array([[0.3, 0.4, 0.0]]))[0]
+    assert abs(Ah[0, 0] - 0.500975006) < 2e-9 and abs(Ah[1, 1] - 1 / math.sqrt(3)) < 1e-9 and abs(Ah[0, 1]) < 1e-12
+
+
+def test_x_only_coefficient_is_exact():
+    """test_integration_poisson.py:398-473: A = 1.1 + x0 has no y-dependence -> A_hom = (1.1 + c_T0) I."""
+    s = PoissonHMM(mesh.create_unit_square(3, 3), Cf.x_only(pufl), lambda x: 1.0, mesh.create_unit_square(7, 7), 0.01)
+    x = np.array([[0.37, 0.1, 0.0], [0.9, 0.5, 0.0]])
+    Ah = s.cell_tensors(x)
+    for k in range(2):
+        assert np.allclose(Ah[k], (1.1 + x[k, 0]) * np.eye(2), atol=1e-14)
+
+
+def test_constant_hooke_equals_plain_fem():
+    """test/integration/test_integration_linear_elasticity.py:205-322 (reference tolerance 1e-4)."""
+    m = mesh.create_box((0, 0, 0), (1.0, 0.2, 0.2), (4, 2, 2))
+    s = LinearElasticityHMM(m, Cf.hooke_const_3d(pufl), lambda x: pufl.as_vector([0.0, 0.0, -1.0]), mesh.create_unit_cube(3, 3, 3), 1.0)
+    s._assemble_stiffness()
+    Cc = np.asarray(Cf.hooke_const_3d(npufl)(np.zeros(3), np.zeros((3, 1))))[..., 0]
+    K = s._A.toarray()
+    Kf = np.zeros_like(K)
+    for nodes in m.cells:
+        verts = m.x[nodes]
+        G = ho.p1_gradients(verts)
+        E = []
+        for a in range(4):
+            for k in range(3):
+                g = np.zeros((3, 3))
+                g[k, :] = G[:, a]
+                E.append(0.5 * (g + g.T))
+        E = np.array(E)
+        dofs = ho.unroll_dofs(nodes, 3)
+        Kf[np.ix_(dofs, dofs)] += ho.simplex_volume(verts) * np.einsum("ijkl,akl,bij->ab", Cc, E, E)
+    assert np.linalg.norm(K - Kf) <= 1e-12 * np.linalg.norm(Kf)
+
+
+def test_elasticity_stratified_fibres_match_oracle():
+    """BASELINE config 4 scaled down: rotated fibres (examples/linear_elasticity/rotated_fibers.py)."""
+    m = mesh.create_box((0, 0, 0), (1.0, 0.4, 0.1), (3, 2, 1))
+    n = 4
+    f = lambda x: pufl.as_vector([0.0, 0.0, -0.05 * 0.4**2])  # noqa: E731  rotated_fibers.py:13-15,88
+    s = LinearElasticityStratifiedHMM(m, Cf.hooke_fibre_3d(pufl), f, mesh.create_unit_cube(n, n, n), 0.01,
+                                      Cf.dtheta_rotation_3d(pufl), petsc_options_cell_problem=TIGHT)  # fmt: skip
+    V = s.function_space
+    clamp = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[0], 0.0))  # rotated_fibers.py:102-115
+    s.set_boundary_conditions(fem.dirichletbc(np.zeros(3), clamp, V))
+    u = s.solve()
+    macro = omesh.create_box([0, 0, 0], [1.0, 0.4, 0.1], [3, 2, 1])
+    mic = ho.MicroCell(omesh.create_unit_cube(n, n, n), "elasticity", 0)
+    Ao = ho.assemble_macro(macro, mic, Cf.hooke_fibre_3d(npufl), 0.01, _np_dtheta("dtheta_rotation_3d"))
+    assert np.linalg.norm((s._A - Ao).toarray()) <= 1e-10 * np.linalg.norm(Ao.toarray())
+    b = ho.assemble_rhs(macro, lambda x: np.array([0.0, 0.0, -0.05 * 0.4**2])[:, None] + 0 * x[:1], 3, degree=1)
+    dofs = ho.unroll_dofs(clamp, 3)
+    uo = ho.solve_dirichlet(Ao, b, dofs, np.zeros(len(dofs)))
+    assert np.abs(u.x.array - uo).max() <= 1e-8 * np.abs(uo).max()
+    assert s.cell_iterations.max() < 10000
