@@ -370,7 +370,9 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         active[qq] = s > P.atol * P.atol;
       }
     }
-    int it = 0;
+    int it = 0, its[NRHS];
+    HMX_UNROLL
+    for (int qq = 0; qq < NRHS; ++qq) its[qq] = 0;
     bool any = false;
     HMX_UNROLL
     for (int qq = 0; qq < NRHS; ++qq) any = any || active[qq];
@@ -457,6 +459,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
             rz[qq] = s;
             const double tol = fmax(P.rtol * P.rtol * rz0[qq], P.atol * P.atol);
             if (!(s > tol)) active[qq] = false;
+            its[qq] = it;
           }
           any = any || active[qq];
         }
@@ -539,6 +542,12 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
           for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
         if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
         if (P.iters != nullptr) P.iters[pt] = it;
+        if (P.work != nullptr) {
+          unsigned long long tot = 0;
+          HMX_UNROLL
+          for (int qq = 0; qq < NRHS; ++qq) tot += (unsigned long long)its[qq];
+          atomic_add_u64(P.work, tot);
+        }
         if (P.resid != nullptr) {
           double worst = 0.0;
           HMX_UNROLL

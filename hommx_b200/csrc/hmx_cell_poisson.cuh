@@ -286,7 +286,9 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
         active[q] = part[q] > P.atol * P.atol;
       }
     }
-    int it = 0;
+    int it = 0, its[NRHS];
+    HMX_UNROLL
+    for (int q = 0; q < NRHS; ++q) its[q] = 0;
     bool any = false;
     HMX_UNROLL
     for (int q = 0; q < NRHS; ++q) any = any || active[q];
@@ -346,6 +348,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
           rz[q] = part[q];
           const double tol = fmax(P.rtol * P.rtol * rz0[q], P.atol * P.atol);
           if (!(part[q] > tol)) active[q] = false;
+          its[q] = it;
         }
         any = any || active[q];
       }
@@ -393,6 +396,12 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
           for (int k = 0; k < D * D; ++k) P.A_hom[pt * D * D + k] = Ah[k];
         if (P.S_loc != nullptr) macro_element_matrix<D, 0>(verts, Ah, P.S_loc + pt * (D + 1) * (D + 1));
         if (P.iters != nullptr) P.iters[pt] = it;
+        if (P.work != nullptr) {
+          unsigned long long tot = 0;
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) tot += (unsigned long long)its[q];
+          atomic_add_u64(P.work, tot);
+        }
         if (P.resid != nullptr) {
           double worst = 0.0;
           HMX_UNROLL

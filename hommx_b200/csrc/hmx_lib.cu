@@ -142,7 +142,7 @@ struct hmx_handle {
   CUfunction fn = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  DevBuf qp, qw, scratch;
+  DevBuf qp, qw, scratch, work;
   // staging for the host-pointer entry points
   DevBuf d_x, d_A, d_it, d_res, d_cells, d_xyz, d_ptr, d_src, d_vals, d_S;
   mutable std::string err;
@@ -210,6 +210,7 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
   P.qp = h->qp.as<double>();
   P.qw = h->qw.as<double>();
   P.scratch = h->scratch.as<double>();
+  P.work = h->work.as<unsigned long long>();
   P.nq = h->nq;
   P.max_it = h->max_it;
   P.rtol = h->rtol;
@@ -328,6 +329,10 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
     fail(h, HMX_ERR_CUDA, "uploading the quadrature table failed: %s", cudaGetErrorString(cudaGetLastError()));
     return bail(HMX_ERR_CUDA);
   }
+  if (h->work.reserve(sizeof(unsigned long long)) != cudaSuccess || cudaMemset(h->work.p, 0, sizeof(unsigned long long)) != cudaSuccess) {
+    fail(h, HMX_ERR_CUDA, "allocating the work counter failed");
+    return bail(HMX_ERR_CUDA);
+  }
   *out = h;
   return HMX_OK;
 }
@@ -336,7 +341,7 @@ void hmx_destroy(hmx_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
+  for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->work, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
                     &h->d_src, &h->d_vals, &h->d_S})
     b->release();
   if (h->module && driver().ok) driver().ModuleUnload(h->module);
@@ -379,6 +384,28 @@ int hmx_kernel_info(const hmx_t* h, int32_t info[8]) {
 int hmx_sync(hmx_t* h) {
   if (!h) return HMX_ERR_ARG;
   HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  return HMX_OK;
+}
+
+int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset) {
+  if (!h || !total) return HMX_ERR_ARG;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  unsigned long long v = 0;
+  HMX_CUDA(h, cudaMemcpyAsync(&v, h->work.p, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+  if (reset) HMX_CUDA(h, cudaMemsetAsync(h->work.p, 0, sizeof v, h->stream));
+  HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  *total = (int64_t)v;
+  return HMX_OK;
+}
+
+int hmx_gather_csr_dev(hmx_t* h, int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src, const double* S_loc,
+                       double* csr_vals) {
+  if (!h) return HMX_ERR_ARG;
+  if (nnz < 0 || (nnz > 0 && (!gather_ptr || !csr_vals))) return fail(h, HMX_ERR_ARG, "hmx_gather_csr: null CSR buffer");
+  if (nnz == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  hmx_gather_csr<<<grid_1d(nnz, 256, h->info[6]), 256, 0, h->stream>>>(nnz, (const long long*)gather_ptr, gather_src, S_loc, csr_vals);
+  HMX_CUDA(h, cudaGetLastError());
   return HMX_OK;
 }
 
@@ -429,12 +456,7 @@ int hmx_assemble_macro_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes,
   }
   int rc = launch_cell(h, n_cells, nullptr, cell_nodes, node_xyz, nullptr, S, iters, resid);
   if (rc != HMX_OK) return rc;
-  if (nnz > 0) {
-    const int g = grid_1d(nnz, 256, h->info[6]);
-    hmx_gather_csr<<<g, 256, 0, h->stream>>>(nnz, (const long long*)gather_ptr, gather_src, S, csr_vals);
-    HMX_CUDA(h, cudaGetLastError());
-  }
-  return HMX_OK;
+  return hmx_gather_csr_dev(h, nnz, gather_ptr, gather_src, S, csr_vals);
 }
 
 int hmx_assemble_macro(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int64_t n_nodes, const double* node_xyz, int64_t nnz,

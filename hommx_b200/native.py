@@ -87,6 +87,8 @@ SYMBOLS = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_assemble_macro_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_gather_csr_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_rhs_iterations": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_measure_peaks": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -288,6 +290,16 @@ class CellSolver:
         self._check(self.lib.hmx_assemble_macro_dev(self._h, int(n_cells), dp(cell_nodes), int(n_nodes), dp(node_xyz), int(nnz),
                                                     dp(gather_ptr), dp(gather_src), dp(csr_vals), dp(S_loc), dp(iters),
                                                     dp(resid)))  # fmt: skip
+
+    def gather_csr_dev(self, nnz, gather_ptr, gather_src, S_loc, csr_vals):
+        dp = self._dp
+        self._check(self.lib.hmx_gather_csr_dev(self._h, int(nnz), dp(gather_ptr), dp(gather_src), dp(S_loc), dp(csr_vals)))
+
+    def rhs_iterations(self, reset=True):
+        """Total PCG iterations (summed over points and right-hand sides) since the last reset."""
+        v = C.c_int64()
+        self._check(self.lib.hmx_rhs_iterations(self._h, C.byref(v), 1 if reset else 0))
+        return v.value
 
     def halo_pack_dev(self, csr_vals, slots, n, buf):
         dp = self._dp

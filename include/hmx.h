@@ -97,6 +97,16 @@ int hmx_assemble_macro_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes,
                            const double* node_xyz, int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src,
                            double* csr_vals, double* S_loc, int32_t* iters, double* resid);
 
+/* The two stages of hmx_assemble_macro_dev can also be run separately: call
+ * hmx_assemble_macro_dev with nnz = 0 (cell kernel only, S_loc required), then this gather. */
+int hmx_gather_csr_dev(hmx_t* h, int64_t nnz, const int64_t* gather_ptr, const int32_t* gather_src, const double* S_loc,
+                       double* csr_vals);
+
+/* Sum over all points and right-hand sides of the PCG iterations executed by the cell kernels
+ * of this handle since the last reset (the "I" of the algorithmic FLOP count).
+ * Synchronises the stream. */
+int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset);
+
 /* Halo exchange helpers for macro cells sharded over several GPUs (the one exchange step of
  * the reference: MatAssembly of shared rows, hmm.py:442).  pack: buf[j] = csr_vals[slots[j]];
  * the caller sums `buf` across ranks (torch.distributed / NCCL all-reduce); unpack writes it

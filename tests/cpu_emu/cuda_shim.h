@@ -52,6 +52,7 @@ inline double warp_sum(double v) {
   }
   return t[me & 31];
 }
+inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline double warp_max(double v) {
   emu::Cta* c = emu::g_cta;
   const int me = c->cur, par = c->wpar[me];

@@ -21,7 +21,7 @@ class CellParams(C.Structure):
     _fields_ = [
         ("n_pts", C.c_int64), ("x_pts", C.c_void_p), ("cell_nodes", C.c_void_p), ("node_xyz", C.c_void_p),
         ("A_hom", C.c_void_p), ("S_loc", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p),
-        ("qp", C.c_void_p), ("qw", C.c_void_p), ("scratch", C.c_void_p),
+        ("qp", C.c_void_p), ("qw", C.c_void_p), ("scratch", C.c_void_p), ("work", C.c_void_p),
         ("nq", C.c_int32), ("max_it", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
     ]  # fmt: skip
 
