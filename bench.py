@@ -56,13 +56,16 @@ WORKLOADS = {
 CELL_RTOL, CELL_ATOL = 1e-8, 1e-10
 
 
+SHRINK = 1
+
+
 def build_solver(wl, world, **kw):
     import hommx_b200 as hx
     from hommx_b200 import mesh
     from hommx_b200 import ufl as pufl
 
     w = WORKLOADS[wl]
-    cells = list(w["cells"])
+    cells = [max(1, c // SHRINK) for c in w["cells"]]
     cells[-1] *= world
     msh = mesh.create_rectangle(*w["box"], cells) if w["dim"] == 2 else mesh.create_box(*w["box"], cells)
     mic = mesh.create_unit_square(w["n"], w["n"]) if w["dim"] == 2 else mesh.create_unit_cube(w["n"], w["n"], w["n"])
@@ -404,7 +407,10 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--shrink", type=int, default=1, help="divide every macro mesh axis by this (ncu --set full captures)")
     args = ap.parse_args()
+    global SHRINK
+    SHRINK = max(1, args.shrink)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

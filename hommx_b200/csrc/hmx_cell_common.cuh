@@ -86,14 +86,67 @@ struct Grid {
   }
 };
 
+// Parity-major node layout used by the matrix-free elasticity kernel: nodes are grouped by the
+// parity of their coordinates (2^D classes of H^D slots, H = ceil(NM/2)).  The threads of a warp
+// sweep cubes of ONE colour (same parities), i.e. origins 2 apart along each axis: in the natural
+// layout corner b of those cubes sits at stride-2/-2NM/-2NM^2 addresses (8-way bank conflicts for
+// n = 8, measured: 66 % of the shared-memory wavefronts of the first version were conflicts); in
+// this layout they are consecutive doubles.  For odd NM the classes are padded (decode -> valid).
+template <int D, int NM>
+struct PGrid {
+  static constexpr int H = (NM + 1) / 2;
+  static constexpr int HC = ipow(H, D);
+  static constexpr int NP = (1 << D) * HC;
+  HMX_DEV static int index(const int (&c)[3]) {
+    int cls = 0, idx = 0, s = 1;
+    HMX_UNROLL
+    for (int a = 0; a < D; ++a) {
+      cls |= (c[a] & 1) << a;
+      idx += (c[a] >> 1) * s;
+      s *= H;
+    }
+    return cls * HC + idx;
+  }
+  HMX_DEV static bool decode(int ip, int (&c)[3]) {
+    const int cls = ip / HC;
+    int r = ip - cls * HC;
+    bool ok = true;
+    HMX_UNROLL
+    for (int a = 0; a < 3; ++a) {
+      c[a] = 0;
+      if (a < D) {
+        c[a] = 2 * (r % H) + ((cls >> a) & 1);
+        r /= H;
+        ok = ok && c[a] < NM;
+      }
+    }
+    return ok;
+  }
+};
+
 // Atoms (the y-dependent scalars of the coefficient) are stored per element on the
 // REDUCED cube set: axes none of the atoms depend on are collapsed, so e.g. a laminate
 // a(y0) costs NM*T evaluations per macro point instead of NM^D*T.
-template <int D, int NM, int YDEP>
+// PARITY = true stores them parity-major like PGrid (restricted to the axes they depend on).
+template <int D, int NM, int YDEP, bool PARITY = false>
 struct AtomIdx {
   static constexpr int NDEP = popcount3(YDEP & ((1 << D) - 1));
-  static constexpr int NRC = ipow(NM, NDEP);
+  static constexpr int H = (NM + 1) / 2;
+  static constexpr int HC = ipow(H, NDEP);
+  static constexpr int NRC = PARITY ? (1 << NDEP) * HC : ipow(NM, NDEP);
   HMX_DEV static int ridx(const int (&c)[3]) {
+    if (PARITY) {
+      int cls = 0, idx = 0, s = 1, bit = 0;
+      HMX_UNROLL
+      for (int a = 0; a < D; ++a)
+        if ((YDEP >> a) & 1) {
+          cls |= (c[a] & 1) << bit;
+          idx += (c[a] >> 1) * s;
+          s *= H;
+          ++bit;
+        }
+      return cls * HC + idx;
+    }
     int r = 0, s = 1;
     HMX_UNROLL
     for (int a = 0; a < D; ++a)
@@ -103,7 +156,24 @@ struct AtomIdx {
       }
     return r;
   }
-  HMX_DEV static void rdecode(int rc, int (&c)[3]) {
+  // reduced slot -> cube coordinates (collapsed axes 0); false for the padding slots of odd NM
+  HMX_DEV static bool rdecode(int rc, int (&c)[3]) {
+    bool ok = true;
+    if (PARITY) {
+      const int cls = rc / HC;
+      int r = rc - cls * HC, bit = 0;
+      HMX_UNROLL
+      for (int a = 0; a < 3; ++a) {
+        c[a] = 0;
+        if (a < D && ((YDEP >> a) & 1)) {
+          c[a] = 2 * (r % H) + ((cls >> bit) & 1);
+          r /= H;
+          ++bit;
+          ok = ok && c[a] < NM;
+        }
+      }
+      return ok;
+    }
     HMX_UNROLL
     for (int a = 0; a < 3; ++a) {
       c[a] = 0;
@@ -112,6 +182,7 @@ struct AtomIdx {
         rc /= NM;
       }
     }
+    return ok;
   }
 };
 

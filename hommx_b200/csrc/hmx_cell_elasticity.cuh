@@ -29,20 +29,21 @@ struct ElasticityLayout {
   static constexpr int N = Grid<D, NM>::N;
   static constexpr int NRHS = D * (D + 1) / 2;
   static constexpr int NV = NRHS;  // Voigt length
-  static constexpr int NDOF = N * D;
+  static constexpr int NP = PGrid<D, NM>::NP;  // node slots of the parity-major layout (>= N)
+  static constexpr int NDOF = NP * D;
   static constexpr int TPR = NT / NRHS;  // threads per right-hand side
   static constexpr int NW = NT / 32;
   static constexpr int WPR = TPR / 32;  // warps per right-hand side
   static constexpr int NA = CO::NATOMS;
   static constexpr int NA1 = NA > 0 ? NA : 1;
   static constexpr int NSYM = D * (D + 1) / 2;
-  static constexpr int NRC = AtomIdx<D, NM, CO::YDEP>::NRC;
+  static constexpr int NRC = AtomIdx<D, NM, CO::YDEP, true>::NRC;
   static constexpr int NCOL = (NM % 2 == 0) ? 2 : 3;  // colours per axis
   static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
   static constexpr int o_red = 0;                              // 2 buffers [NW][NREDV]
   static constexpr int o_atoms = o_red + 2 * NW * NREDV;       // [NA][T][NRC]
-  static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][N] inverse diagonal blocks
-  static constexpr int o_p = o_dinv + NSYM * N;                // [NRHS][D][N]
+  static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][NP] inverse diagonal blocks
+  static constexpr int o_p = o_dinv + NSYM * NP;               // [NRHS][D][NP]
   static constexpr int o_y = o_p + NRHS * NDOF;                // [NRHS][D][N]
   static constexpr int total = o_y + NRHS * NDOF;
   static constexpr int scratch_doubles = 2 * NRHS * NDOF;      // x and r per CTA
@@ -81,8 +82,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
                               const double* s_p, double* s_y, int q, int l) {
   using L = ElasticityLayout<CO, NM, NT>;
   using G = Grid<CO::DIM, NM>;
-  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
-  constexpr int D = L::D, T = L::T, N = L::N, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC, NCOL = L::NCOL;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
+  using PG = PGrid<CO::DIM, NM>;
+  constexpr int D = L::D, T = L::T, N = L::NP, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC, NCOL = L::NCOL;
   constexpr int NC = 1 << D;  // corners
   constexpr int HALF = NM / 2;  // size of colour classes 0 and 1 (class 2, odd n only: the last index)
   const double h = 1.0 / (double)NM;
@@ -113,7 +115,11 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
       }
       int node[NC];
       HMX_UNROLL
-      for (int b = 0; b < NC; ++b) node[b] = G::template shifted<1>(o, b);
+      for (int b = 0; b < NC; ++b) {
+        int cb[3];
+        G::template shift_coords<1>(o, b, cb);
+        node[b] = PG::index(cb);
+      }
       double u[NC][D], acc[NC][D];
       HMX_UNROLL
       for (int b = 0; b < NC; ++b)
@@ -202,8 +208,11 @@ template <class CO, int NM, int NT>
 HMX_DEV void elasticity_cell_body(const CellParams& P) {
   using L = ElasticityLayout<CO, NM, NT>;
   using G = Grid<CO::DIM, NM>;
-  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
-  constexpr int D = L::D, T = L::T, N = L::N, NRHS = L::NRHS, NV = L::NV, NDOF = L::NDOF, TPR = L::TPR, NW = L::NW;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
+  using PG = PGrid<CO::DIM, NM>;
+  // N counts node SLOTS of the parity-major layout; padding slots (odd NM) hold zeros in every vector
+  // and in the preconditioner, so the vector loops need no validity test.
+  constexpr int D = L::D, T = L::T, N = L::NP, NRHS = L::NRHS, NV = L::NV, NDOF = L::NDOF, TPR = L::TPR, NW = L::NW;
   constexpr int WPR = L::WPR, NA = L::NA, NA1 = L::NA1, NSYM = L::NSYM, NRC = L::NRC;
   constexpr int NPT = (N + TPR - 1) / TPR;  // nodes per thread within its right-hand side
   constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
@@ -239,11 +248,11 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       for (int idx = t_id; idx < T * NRC; idx += NT) {
         const int t = idx / NRC, rc = idx - t * NRC;
         int c[3];
-        AI::rdecode(rc, c);
+        const bool real_slot = AI::rdecode(rc, c);
         double acc[NA1];
         HMX_UNROLL
         for (int k = 0; k < NA1; ++k) acc[k] = 0.0;
-        for (int qq = 0; qq < P.nq; ++qq) {
+        for (int qq = 0; real_slot && qq < P.nq; ++qq) {
           double y[D], s[NA1];
           HMX_UNROLL
           for (int a = 0; a < D; ++a) y[a] = ((double)c[a] + P.qp[(t * P.nq + qq) * D + a]) * h;
@@ -271,11 +280,15 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       }
       block_sum<NA1, NW>(smean, s_red + (red_flip ^= 1) * NW * L::NREDV);
       HMX_UNROLL
-      for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * NRC);
+      for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * ipow(NM, AI::NDEP));  // padding slots hold 0
     }
     for (int i = t_id; i < N; i += NT) {
       int c[3];
-      G::decode(i, c);
+      if (!PG::decode(i, c)) {
+        HMX_UNROLL
+        for (int k = 0; k < NSYM; ++k) s_dinv[k * N + i] = 0.0;
+        continue;
+      }
       double blk[NSYM];
       HMX_UNROLL
       for (int k = 0; k < NSYM; ++k) blk[k] = 0.0;
