@@ -387,6 +387,12 @@ def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
             f"    M[{p * dim + i}] = {1.0 if p == i else 0.0};" for p in range(dim) for i in range(dim)
         )
 
+    # structurally zero entries of M (bit p*dim+i): the kernels drop those terms at compile time
+    if dth is not None:
+        mzero = sum(1 << k for k, e in enumerate(dth) if e.is_const() and e.value == 0.0)
+    else:
+        mzero = sum(1 << (p * dim + i) for p in range(dim) for i in range(dim) if p != i)
+
     fn = "  __device__ __forceinline__ static void"
     src = f"""// hommx_b200 coefficient program v1
 struct HMX_COEFF {{
@@ -399,6 +405,7 @@ struct HMX_COEFF {{
   static constexpr int SCALAR = {1 if scalar else 0};
   static constexpr int QDEG = {degree};
   static constexpr int YDEP = {ydep};
+  static constexpr unsigned MZERO = {mzero}u;
 {fn} point_consts(const double* __restrict__ x, double* __restrict__ pc) {{
     (void)x; (void)pc;
 {pc_body}

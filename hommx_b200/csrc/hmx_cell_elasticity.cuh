@@ -13,8 +13,13 @@
 //   t_k = |e| n sigma Mcol_{pi(k)};   y_{P(k+1)} += t_k,  y_{P(k)} -= t_k.
 // Cubes are processed colour by colour (2^D colours for even n) so that the in-place
 // accumulation into the shared-memory result needs no atomics and is deterministic.
-// Threads are grouped by right-hand side (NT = NRHS * TPR); search directions p and the product
-// y = K p live in shared memory, the residuals and correctors in an L2-resident per-CTA scratch.
+// Threads are grouped by right-hand side (NT = NRHS * TPR).  The right-hand sides are independent
+// linear systems, so each group runs ITS OWN PCG loop and synchronises only with itself through a
+// named barrier (BAR.SYNC id, TPR): the groups drift apart and fill each other's barrier and
+// reduction bubbles on the FP64 pipe.  Search directions p and the product y = K p live in shared
+// memory, the residuals and correctors in an L2-resident per-CTA scratch.  Structurally zero
+// entries of M (known when the coefficient program is generated, CO::MZERO) are dropped from the
+// element kernel at compile time.
 // Preconditioner: D x D block Jacobi.  Epilogue as in the Poisson kernel:
 //   A_hom[p][q] = <C>[p][q] - b_p.x_q - x_p.r_q.
 #pragma once
@@ -41,7 +46,8 @@ struct ElasticityLayout {
   static constexpr int NCOL = (NM % 2 == 0) ? 2 : 3;  // colours per axis
   static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
   static constexpr int o_red = 0;                              // 2 buffers [NW][NREDV]
-  static constexpr int o_atoms = o_red + 2 * NW * NREDV;       // [NA][T][NRC]
+  static constexpr int o_stat = o_red + 2 * NW * NREDV;        // [NRHS][4] per right-hand side: its, rz, rz0
+  static constexpr int o_atoms = o_stat + 4 * NRHS;            // [NA][T][NRC]
   static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][NP] inverse diagonal blocks
   static constexpr int o_p = o_dinv + NSYM * NP;               // [NRHS][D][NP]
   static constexpr int o_y = o_p + NRHS * NDOF;                // [NRHS][D][N]
@@ -75,20 +81,20 @@ HMX_DEV void sym_inverse(const double* a, double* inv) {
   }
 }
 
-// One sweep over the cubes: y += K p  (RHSMODE = false)  or  y += b_q  (RHSMODE = true: the
-// strain of every element is the unit strain E_q and the sign is flipped; hmm.py:898-903).
+// One sweep over the cubes by the TPR threads of right-hand side q:  y += K p  (RHSMODE = false)
+// or  y += b_q  (RHSMODE = true: every element carries the unit strain -E_q; hmm.py:898-903).
+// Ms = sqrt(|e|) n M, so that e and sigma both carry sqrt(|e|) and the nodal forces the full |e|.
 template <class CO, int NM, int NT, bool RHSMODE>
-HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO::DIM], const double* s_atoms,
-                              const double* s_p, double* s_y, int q, int l) {
+HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
+                              const double* s_p, double* s_y, int q, int l, double sqrtw) {
   using L = ElasticityLayout<CO, NM, NT>;
   using G = Grid<CO::DIM, NM>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
   using PG = PGrid<CO::DIM, NM>;
   constexpr int D = L::D, T = L::T, N = L::NP, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC, NCOL = L::NCOL;
-  constexpr int NC = 1 << D;  // corners
+  constexpr int NC = 1 << D;    // corners
   constexpr int HALF = NM / 2;  // size of colour classes 0 and 1 (class 2, odd n only: the last index)
-  const double h = 1.0 / (double)NM;
-  const double w = (D == 2 ? 0.5 * h * h : h * h * h / 6.0);  // |e|; Mn already carries the factor n
+#define HMX_MZ(p_, ax_) ((CO::MZERO >> ((p_)*D + (ax_))) & 1u)
 
   for (int col = 0; col < ipow(NCOL, D); ++col) {
     int cls[3], cnt[3], total = 1;
@@ -134,9 +140,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
         double e[NV];
         if (RHSMODE) {
           HMX_UNROLL
-          for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -1.0 : 0.0;
+          for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -sqrtw : 0.0;
         } else {
-          // H[p][j] = sum_k Mn[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j])
+          // H[p][j] = sum_k Ms[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j])
           double H[D][D];
           HMX_UNROLL
           for (int p = 0; p < D; ++p)
@@ -150,7 +156,8 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
             for (int j = 0; j < D; ++j) {
               const double dk = u[b1][j] - u[b0][j];
               HMX_UNROLL
-              for (int p = 0; p < D; ++p) H[p][j] += Mn[p * D + ax] * dk;
+              for (int p = 0; p < D; ++p)
+                if (!HMX_MZ(p, ax)) H[p][j] += Ms[p * D + ax] * dk;
             }
           }
           HMX_UNROLL
@@ -170,14 +177,14 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
         CO::stress(pc, sa, e, sig);
         double S[D][D];
         HMX_UNROLL
-        for (int v = 0; v < D; ++v) S[v][v] = w * sig[v];
+        for (int v = 0; v < D; ++v) S[v][v] = sig[v];
         {
           int v = D;
           HMX_UNROLL
           for (int r = 0; r < D; ++r)
             HMX_UNROLL
             for (int c = r + 1; c < D; ++c) {
-              S[r][c] = S[c][r] = w * sig[v];
+              S[r][c] = S[c][r] = sig[v];
               ++v;
             }
         }
@@ -189,7 +196,8 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
           for (int j = 0; j < D; ++j) {
             double tk = 0.0;
             HMX_UNROLL
-            for (int p = 0; p < D; ++p) tk += S[j][p] * Mn[p * D + ax];
+            for (int p = 0; p < D; ++p)
+              if (!HMX_MZ(p, ax)) tk += S[j][p] * Ms[p * D + ax];
             acc[b1][j] += tk;
             acc[b0][j] -= tk;
           }
@@ -200,8 +208,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Mn)[CO::DIM * CO:
         HMX_UNROLL
         for (int j = 0; j < D; ++j) s_y[(q * D + j) * N + node[b]] += acc[b][j];
     }
-    sync();
+    group_sync(1 + q, L::TPR);
   }
+#undef HMX_MZ
 }
 
 template <class CO, int NM, int NT>
@@ -214,16 +223,17 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   // and in the preconditioner, so the vector loops need no validity test.
   constexpr int D = L::D, T = L::T, N = L::NP, NRHS = L::NRHS, NV = L::NV, NDOF = L::NDOF, TPR = L::TPR, NW = L::NW;
   constexpr int WPR = L::WPR, NA = L::NA, NA1 = L::NA1, NSYM = L::NSYM, NRC = L::NRC;
-  constexpr int NPT = (N + TPR - 1) / TPR;  // nodes per thread within its right-hand side
+  constexpr int NPT = (N + TPR - 1) / TPR;  // node slots per thread within its right-hand side
   constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
 
   double* sm = dyn_smem();
   double* s_red = sm + L::o_red;
+  double* s_stat = sm + L::o_stat;
   double* s_atoms = sm + L::o_atoms;
   double* s_dinv = sm + L::o_dinv;
   double* s_p = sm + L::o_p;
   double* s_y = sm + L::o_y;
-  double* g_x = P.scratch + (size_t)bid() * L::scratch_doubles;  // [NRHS][D][N]
+  double* g_x = P.scratch + (size_t)bid() * L::scratch_doubles;  // [NRHS][D][NP]
   double* g_r = g_x + NRHS * NDOF;
 
   const int t_id = tid();
@@ -231,6 +241,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   const int lane = t_id & 31, warp = t_id >> 5;
   const double h = 1.0 / (double)NM;
   const double vol = (D == 2 ? 0.5 * h * h : h * h * h / 6.0);
+  const double sqrtw = sqrt(vol);
   int red_flip = 0;
 
   for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {
@@ -238,10 +249,13 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     macro_point<D>(P, pt, xm, verts);
     double pc[NPC1];
     CO::point_consts(xm, pc);
-    double Mn[D * D];  // n * M,  M[p*D+i] = d theta_i / d x_p  (hmm.py:1015-1016)
+    double Mn[D * D], Ms[D * D];  // n M and sqrt(|e|) n M;  M[p*D+i] = d theta_i / d x_p  (hmm.py:1015-1016)
     CO::dtheta(xm, Mn);
     HMX_UNROLL
-    for (int k = 0; k < D * D; ++k) Mn[k] *= (double)NM;
+    for (int k = 0; k < D * D; ++k) {
+      Mn[k] *= (double)NM;
+      Ms[k] = Mn[k] * sqrtw;
+    }
 
     // ---- 1. atoms ----
     if (NA > 0) {
@@ -265,8 +279,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         for (int k = 0; k < NA; ++k) s_atoms[(k * T + t) * NRC + rc] = acc[k];
       }
     }
-    // zero the accumulation target
-    for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;
+    for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;  // the accumulation target
     sync();
 
     // ---- 2. atom means, block-Jacobi preconditioner ----
@@ -341,11 +354,22 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       HMX_UNROLL
       for (int k = 0; k < NSYM; ++k) s_dinv[k * N + i] = inv[k];
     }
+    sync();  // the preconditioner is complete before any group starts
 
-    // ---- 3. right-hand sides b_q -> y, r = b, z = Dinv r, p = z ----
-    elasticity_sweep<CO, NM, NT, true>(pc, Mn, s_atoms, s_p, s_y, q, l);  // ends with a barrier
-    double rz[NRHS], rz0[NRHS];
-    bool active[NRHS];
+    // ---- 3./4. one PCG per right-hand side, each group on its own named barrier ----
+    // group-wide sum of one value per thread; buffers alternate so no trailing barrier is needed
+    auto group_sum = [&](double v) {
+      v = warp_sum(v);
+      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+      if (lane == 0) buf[warp] = v;
+      group_sync(1 + q, TPR);
+      double s = 0.0;
+      HMX_UNROLL
+      for (int ww = 0; ww < WPR; ++ww) s += buf[q * WPR + ww];
+      return s;
+    };
+    elasticity_sweep<CO, NM, NT, true>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
+    double rz, rz0;
     {
       double part = 0.0;
       HMX_UNROLL
@@ -370,144 +394,84 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
           }
         }
       }
-      part = warp_sum(part);
-      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
-      if (lane == 0) buf[warp] = part;
-      sync();
-      HMX_UNROLL
-      for (int qq = 0; qq < NRHS; ++qq) {
-        double s = 0.0;
-        HMX_UNROLL
-        for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
-        rz[qq] = rz0[qq] = s;
-        active[qq] = s > P.atol * P.atol;
-      }
+      rz = rz0 = group_sum(part);  // its barrier also publishes p and the zeroed y
     }
-    int it = 0, its[NRHS];
-    HMX_UNROLL
-    for (int qq = 0; qq < NRHS; ++qq) its[qq] = 0;
-    bool any = false;
-    HMX_UNROLL
-    for (int qq = 0; qq < NRHS; ++qq) any = any || active[qq];
-
-    // ---- 4. PCG ----
-    while (any && it < P.max_it) {
+    int it = 0;
+    bool active = rz0 > P.atol * P.atol;
+    const double tol2 = fmax(P.rtol * P.rtol * rz0, P.atol * P.atol);
+    while (active && it < P.max_it) {
       ++it;
-      elasticity_sweep<CO, NM, NT, false>(pc, Mn, s_atoms, s_p, s_y, q, l);  // y = K p
-      double pAp[NRHS];
-      {
-        double part = 0.0;
-        HMX_UNROLL
-        for (int j = 0; j < NPT; ++j) {
-          const int i = l + j * TPR;
-          if (i < N) {
+      elasticity_sweep<CO, NM, NT, false>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
+      double part = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) part += s_p[(q * D + c) * N + i] * s_y[(q * D + c) * N + i];
+        }
+      }
+      const double pAp = group_sum(part);
+      const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
+      part = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          double r[D];
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            const int a = (q * D + c) * N + i;
+            const double yv = s_y[a];
+            s_y[a] = 0.0;
+            g_x[a] += alpha * s_p[a];
+            r[c] = g_r[a] - alpha * yv;
+            g_r[a] = r[c];
+          }
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            double z = 0.0;
             HMX_UNROLL
-            for (int c = 0; c < D; ++c) part += s_p[(q * D + c) * N + i] * s_y[(q * D + c) * N + i];
+            for (int c2 = 0; c2 < D; ++c2) z += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
+            part += r[c] * z;
           }
         }
-        part = warp_sum(part);
-        double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
-        if (lane == 0) buf[warp] = part;
-        sync();
-        HMX_UNROLL
-        for (int qq = 0; qq < NRHS; ++qq) {
-          double s = 0.0;
-          HMX_UNROLL
-          for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
-          pAp[qq] = s;
-        }
       }
-      double alpha_all[NRHS];
-      HMX_UNROLL
-      for (int qq = 0; qq < NRHS; ++qq) alpha_all[qq] = (active[qq] && pAp[qq] > 0.0) ? rz[qq] / pAp[qq] : 0.0;
-      double alpha = 0.0;
-      bool mine = false;
-      HMX_UNROLL
-      for (int qq = 0; qq < NRHS; ++qq)
-        if (qq == q) {
-          alpha = alpha_all[qq];
-          mine = active[qq];
-        }
-      {
-        double part = 0.0;
+      const double rz_new = group_sum(part);
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      if (!(rz_new > tol2)) {
+        active = false;
+      } else {
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j) {
           const int i = l + j * TPR;
           if (i < N) {
             double r[D];
             HMX_UNROLL
-            for (int c = 0; c < D; ++c) {
-              const int a = (q * D + c) * N + i;
-              const double yv = s_y[a];
-              s_y[a] = 0.0;
-              r[c] = g_r[a];
-              if (mine) {
-                g_x[a] += alpha * s_p[a];
-                r[c] -= alpha * yv;
-                g_r[a] = r[c];
-              }
-            }
+            for (int c = 0; c < D; ++c) r[c] = g_r[(q * D + c) * N + i];
             HMX_UNROLL
             for (int c = 0; c < D; ++c) {
               double z = 0.0;
               HMX_UNROLL
               for (int c2 = 0; c2 < D; ++c2) z += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
-              part += r[c] * z;
+              const int a = (q * D + c) * N + i;
+              s_p[a] = z + beta * s_p[a];
             }
           }
         }
-        part = warp_sum(part);
-        double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
-        if (lane == 0) buf[warp] = part;
-        sync();
-        any = false;
-        double beta = 0.0;
-        HMX_UNROLL
-        for (int qq = 0; qq < NRHS; ++qq) {
-          double s = 0.0;
-          HMX_UNROLL
-          for (int ww = 0; ww < WPR; ++ww) s += buf[qq * WPR + ww];
-          if (active[qq]) {
-            if (qq == q) beta = s / rz[qq];
-            rz[qq] = s;
-            const double tol = fmax(P.rtol * P.rtol * rz0[qq], P.atol * P.atol);
-            if (!(s > tol)) active[qq] = false;
-            its[qq] = it;
-          }
-          any = any || active[qq];
-        }
-        if (any) {
-          bool still = false;
-          HMX_UNROLL
-          for (int qq = 0; qq < NRHS; ++qq)
-            if (qq == q) still = active[qq];
-          if (still) {
-            HMX_UNROLL
-            for (int j = 0; j < NPT; ++j) {
-              const int i = l + j * TPR;
-              if (i < N) {
-                double r[D];
-                HMX_UNROLL
-                for (int c = 0; c < D; ++c) r[c] = g_r[(q * D + c) * N + i];
-                HMX_UNROLL
-                for (int c = 0; c < D; ++c) {
-                  double z = 0.0;
-                  HMX_UNROLL
-                  for (int c2 = 0; c2 < D; ++c2) z += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
-                  const int a = (q * D + c) * N + i;
-                  s_p[a] = z + beta * s_p[a];
-                }
-              }
-            }
-          }
-          sync();
-        }
+        group_sync(1 + q, TPR);
       }
+    }
+    if (l == 0) {
+      s_stat[4 * q + 0] = (double)it;
+      s_stat[4 * q + 1] = rz;
+      s_stat[4 * q + 2] = rz0;
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
-    sync();  // x and r of every right-hand side are visible to the whole CTA
-    elasticity_sweep<CO, NM, NT, true>(pc, Mn, s_atoms, s_p, s_y, q, l);
+    elasticity_sweep<CO, NM, NT, true>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
+    sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {
       double z[2 * NRHS];
       HMX_UNROLL
@@ -521,15 +485,18 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
             const double xq = g_x[(q * D + c) * N + i], rq = g_r[(q * D + c) * N + i];
             HMX_UNROLL
             for (int p = 0; p < NRHS; ++p) {
-              z[p] += s_y[(p * D + c) * N + i] * xq;           // b_p . x_q
-              z[NRHS + p] += g_x[(p * D + c) * N + i] * rq;    // x_p . r_q
+              z[p] += s_y[(p * D + c) * N + i] * xq;         // b_p . x_q
+              z[NRHS + p] += g_x[(p * D + c) * N + i] * rq;  // x_p . r_q
             }
           }
         }
       }
       HMX_UNROLL
       for (int k = 0; k < 2 * NRHS; ++k) z[k] = warp_sum(z[k]);
-      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+      // the groups did different numbers of reductions: after the barrier above every thread
+      // restarts from the same buffer parity
+      red_flip = 0;
+      double* buf = s_red;
       if (lane == 0) {
         HMX_UNROLL
         for (int k = 0; k < 2 * NRHS; ++k) buf[warp * L::NREDV + k] = z[k];
@@ -554,24 +521,21 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         if (P.A_hom != nullptr)
           for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
         if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
-        if (P.iters != nullptr) P.iters[pt] = it;
-        if (P.work != nullptr) {
-          unsigned long long tot = 0;
-          HMX_UNROLL
-          for (int qq = 0; qq < NRHS; ++qq) tot += (unsigned long long)its[qq];
-          atomic_add_u64(P.work, tot);
+        int itmax = 0;
+        unsigned long long tot = 0;
+        double worst = 0.0;
+        for (int qq = 0; qq < NRHS; ++qq) {
+          const int iq = (int)s_stat[4 * qq];
+          itmax = iq > itmax ? iq : itmax;
+          tot += (unsigned long long)iq;
+          if (s_stat[4 * qq + 2] > P.atol * P.atol) worst = fmax(worst, sqrt(s_stat[4 * qq + 1] / s_stat[4 * qq + 2]));
         }
-        if (P.resid != nullptr) {
-          double worst = 0.0;
-          HMX_UNROLL
-          for (int qq = 0; qq < NRHS; ++qq)
-            if (rz0[qq] > P.atol * P.atol) worst = fmax(worst, sqrt(rz[qq] / rz0[qq]));
-          P.resid[pt] = worst;
-        }
+        if (P.iters != nullptr) P.iters[pt] = itmax;
+        if (P.resid != nullptr) P.resid[pt] = worst;
+        if (P.work != nullptr) atomic_add_u64(P.work, tot);
       }
     }
-    sync();
-    // leave y zeroed for the next macro point (done at the top of the loop)
+    sync();  // shared memory and the scratch are reused by the next macro point
   }
 }
 

@@ -23,6 +23,8 @@ HMX_DEV int tid() { return threadIdx.x; }
 HMX_DEV int bid() { return blockIdx.x; }
 HMX_DEV int nblocks() { return gridDim.x; }
 HMX_DEV void sync() { __syncthreads(); }  // BAR.SYNC
+// named barrier `id` (1..15) over `count` threads (a multiple of 32): BAR.SYNC id, count
+HMX_DEV void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 HMX_DEV double* dyn_smem() {
   extern __shared__ __align__(16) double hmx_smem_[];
   return hmx_smem_;

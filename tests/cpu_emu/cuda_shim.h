@@ -25,6 +25,8 @@ struct Cta {
   double* smem;
   double* wbuf;  // [2][nthreads] warp collective exchange
   int* wpar;     // [nthreads] per-fiber parity
+  int arrived[64];       // barrier id -> fibers waiting
+  unsigned gen[64];      // barrier id -> generation
 };
 extern thread_local Cta* g_cta;
 void yield();  // return to the scheduler until every fiber has arrived
@@ -33,14 +35,27 @@ void yield();  // return to the scheduler until every fiber has arrived
 inline int tid() { return emu::g_cta->cur; }
 inline int bid() { return emu::g_cta->bid; }
 inline int nblocks() { return emu::g_cta->nblocks; }
-inline void sync() { emu::yield(); }
+// barrier `id` over `count` fibers (ids 0..15 mirror the hardware named barriers, 16.. are the
+// per-warp rendezvous of the shuffle emulation)
+inline void barrier(int id, int count) {
+  emu::Cta* c = emu::g_cta;
+  const unsigned g = c->gen[id];
+  if (++c->arrived[id] == count) {
+    c->arrived[id] = 0;
+    c->gen[id] = g + 1;
+  } else {
+    while (c->gen[id] == g) emu::yield();
+  }
+}
+inline void sync() { barrier(0, emu::g_cta->nthreads); }
+inline void group_sync(int id, int count) { barrier(id, count); }
 inline double* dyn_smem() { return emu::g_cta->smem; }
 inline double warp_sum(double v) {
   emu::Cta* c = emu::g_cta;
   const int me = c->cur, par = c->wpar[me];
   c->wbuf[par * c->nthreads + me] = v;
   c->wpar[me] = par ^ 1;
-  emu::yield();
+  barrier(16 + me / 32, 32);
   const int w0 = (me / 32) * 32;
   // same association as the xor butterfly of the device code
   double t[32];
@@ -58,7 +73,7 @@ inline double warp_max(double v) {
   const int me = c->cur, par = c->wpar[me];
   c->wbuf[par * c->nthreads + me] = v;
   c->wpar[me] = par ^ 1;
-  emu::yield();
+  barrier(16 + me / 32, 32);
   const int w0 = (me / 32) * 32;
   double m = c->wbuf[par * c->nthreads + w0];
   for (int l = 1; l < 32; ++l) m = fmax(m, c->wbuf[par * c->nthreads + w0 + l]);

@@ -43,6 +43,8 @@ inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, voi
   cta.bid = bid;
   cta.nblocks = nblocks;
   cta.cur = 0;
+  std::memset(cta.arrived, 0, sizeof cta.arrived);
+  std::memset(cta.gen, 0, sizeof cta.gen);
   std::vector<double> smem(smem_doubles + 2, 0.0), wbuf(2 * nthreads, 0.0);
   std::vector<int> wpar(nthreads, 0);
   cta.smem = smem.data();
