@@ -26,7 +26,7 @@ import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
-from . import assembly, codegen, fem, micro, native, quadrature
+from . import assembly, codegen, fem, micro, native, parallel, quadrature
 from .mesh import as_simplex_mesh
 
 _CELL_OPTION_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it"}
@@ -63,6 +63,7 @@ class BaseHMM:
         Dtheta_transpose=None,
         quadrature_rule=None,
         device=None,
+        shard=True,
     ):
         self._logger = logging.getLogger(__name__)
         self._msh = as_simplex_mesh(msh)
@@ -122,6 +123,7 @@ class BaseHMM:
         self._A_values = np.zeros(self._pattern.nnz)
         self._A = None
         self._device = device
+        self._shard = bool(shard)  # False: assemble every macro cell on this GPU even if torch.distributed is up
         self._solver = None
         self._dev = None
         self._rank, self._world = 0, 1
@@ -152,7 +154,7 @@ class BaseHMM:
 
         if not torch.cuda.is_available():
             raise native.HmxError("no CUDA device: the HMM hot path runs on the GPU only (there is no CPU fallback)")
-        if dist.is_available() and dist.is_initialized():
+        if self._shard and dist.is_available() and dist.is_initialized():
             self._rank, self._world = dist.get_rank(), dist.get_world_size()
         dev = self._device
         if dev is None:
@@ -180,7 +182,8 @@ class BaseHMM:
         if self._world > 1:
             sh = assembly.shared_slots(self._pattern.slot_map, n_cells, self._world, self._pattern.nnz)
             d["shared"] = torch.as_tensor(sh, device=tdev)
-            d["halo"] = torch.zeros(len(sh), dtype=torch.float64, device=tdev)
+            d["halo"] = parallel.HaloExchange(d["shared"], torch.zeros(len(sh), dtype=torch.float64, device=tdev),
+                                              self._solver.halo_pack_dev, self._solver.halo_unpack_dev)
         self._dev = d
 
     # ------------------------------------------------------------------ hot path
@@ -216,15 +219,7 @@ class BaseHMM:
 
     def _halo_sum(self):
         """Sum of the value slots shared between ranks: the only collective of the path."""
-        import torch.distributed as dist
-
-        d = self._dev
-        n = d["shared"].numel()
-        if n == 0:
-            return
-        self._solver.halo_pack_dev(d["vals"], d["shared"], n, d["halo"])
-        dist.all_reduce(d["halo"], op=dist.ReduceOp.SUM)
-        self._solver.halo_unpack_dev(d["vals"], d["shared"], n, d["halo"])
+        self._dev["halo"].sum(self._dev["vals"])
 
     def _full_values(self):
         """Complete CSR values on every rank for the (host, scipy) macro solve; outside the hot path.
