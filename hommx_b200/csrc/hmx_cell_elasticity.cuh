@@ -96,9 +96,18 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
   constexpr int HALF = NM / 2;  // size of colour classes 0 and 1 (class 2, odd n only: the last index)
 #define HMX_MZ(p_, ax_) ((CO::MZERO >> ((p_)*D + (ax_))) & 1u)
 
-  for (int col = 0; col < ipow(NCOL, D); ++col) {
+  // SLAB scheme (even NM, last-axis half-count divisible by the warps of the group): colours are
+  // ordered with the parity of the last axis outermost and every warp owns a slab of last-axis
+  // indices.  Inside one last-axis parity the warps then write disjoint node planes, so the
+  // colours of that parity only need the warp's own lock-step order (__syncwarp) and the group
+  // barrier is needed twice per sweep instead of 2^D times.
+  constexpr bool SLAB = (NM % 2 == 0) && (HALF % L::WPR == 0);
+  constexpr int NCOLT = ipow(NCOL, D);
+  const int wig = l >> 5, lig = l & 31;  // warp within the group, lane
+  for (int col = 0; col < NCOLT; ++col) {
     int cls[3], cnt[3], total = 1;
     {
+      // the last axis parity is the slowest digit of `col`
       int r = col;
       HMX_UNROLL
       for (int a = 0; a < 3; ++a) {
@@ -108,7 +117,12 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         total *= cnt[a];
       }
     }
-    for (int k = l; k < total; k += L::TPR) {
+    // SLAB: this warp's share of the colour = its slab of the last axis
+    const int slab = SLAB ? total / L::WPR : total;
+    const int kbeg = SLAB ? wig * slab + lig : l;
+    const int kend = SLAB ? (wig + 1) * slab : total;
+    const int kstep = SLAB ? 32 : L::TPR;
+    for (int k = kbeg; k < kend; k += kstep) {
       int o[3];
       {
         int r = k;
@@ -208,7 +222,10 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         HMX_UNROLL
         for (int j = 0; j < D; ++j) s_y[(q * D + j) * N + node[b]] += acc[b][j];
     }
-    group_sync(1 + q, L::TPR);
+    if (SLAB && (col + 1) % (NCOLT / NCOL) != 0)
+      warp_sync();  // next colour has the same last-axis parity: only this warp's order matters
+    else
+      group_sync(1 + q, L::TPR);
   }
 #undef HMX_MZ
 }

@@ -4,10 +4,14 @@
 //        -DHMX_COEFF_FILE="<generated struct HMX_COEFF>" -DHMX_KIND=k -DHMX_NM=n -DHMX_NT=threads
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
+#ifndef HMX_VARIANT
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator streamed from L2
+#endif
 #if HMX_KIND == 0
 #include "hmx_cell_poisson.cuh"
 #else
 #include "hmx_cell_elasticity.cuh"
+#include "hmx_cell_elasticity_asm.cuh"
 #endif
 #include HMX_COEFF_FILE
 
@@ -18,6 +22,8 @@
 namespace {
 #if HMX_KIND == 0
 using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+#elif HMX_VARIANT == 1
+using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #else
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #endif
@@ -30,6 +36,8 @@ constexpr int kScratch = Layout::scratch_doubles;
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #if HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 1
+  hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #endif
@@ -43,6 +51,8 @@ static void emu_body(void* arg) {
   const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
 #if HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 1
+  hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #endif

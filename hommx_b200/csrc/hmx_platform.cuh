@@ -25,6 +25,16 @@ HMX_DEV int nblocks() { return gridDim.x; }
 HMX_DEV void sync() { __syncthreads(); }  // BAR.SYNC
 // named barrier `id` (1..15) over `count` threads (a multiple of 32): BAR.SYNC id, count
 HMX_DEV void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+HMX_DEV void warp_sync() { __syncwarp(); }
+// streaming load that bypasses L1 (the per-point matrix is far larger than L1): LDG.E.64.STRONG.GPU / ld.global.cg
+HMX_DEV double ld_stream(const double* p) { return __ldcg(p); }
+// 16-byte variants (LDG.E.128 / STG.E.128); the address must be 16-byte aligned
+HMX_DEV void ld_stream_pair(const double* p, double& a, double& b) {
+  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  a = v.x;
+  b = v.y;
+}
+HMX_DEV void st_pair(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 HMX_DEV double* dyn_smem() {
   extern __shared__ __align__(16) double hmx_smem_[];
   return hmx_smem_;

@@ -26,7 +26,10 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-_HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh", "hmx_cell_entry.cu")
+_HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh",
+            "hmx_cell_elasticity_asm.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, ASSEMBLED = 0, 1
+SMEM_LIMIT = 227 * 1024
 
 
 class HmxError(RuntimeError):
@@ -115,11 +118,30 @@ def load_library():
 # ----------------------------------------------------------------------------
 # cell kernels
 # ----------------------------------------------------------------------------
-def default_threads(dim, kind, n):
+def default_variant(prog, n):
+    """Elasticity: stream the assembled operator from L2 when one thread per node is possible and p, x
+    fit in shared memory (n <= 8 in 3-D); otherwise the matrix-free element kernel."""
+    if prog.kind == POISSON:
+        return MATRIX_FREE
+    d = prog.dim
+    N = n**d
+    nvec = d * d * (d + 1) // 2
+    smem = 8 * (2 * N * nvec + d * (d + 1) // 2 * N + max(1, prog.natoms) * (2 if d == 2 else 6) * N + 1024)
+    fits = N <= 1024 and smem <= SMEM_LIMIT
+    # measured on B200 (C4): the assembled variant reaches 33.4k cell solves/s against 36.4k of the
+    # matrix-free kernel (L2 latency is not hidden by 16 warps at 128 registers) -> opt-in only
+    return ASSEMBLED if (fits and os.environ.get("HMX_ELASTICITY_VARIANT") == "assembled") else MATRIX_FREE
+
+
+def default_threads(dim, kind, n, variant=MATRIX_FREE):
     """Threads per CTA for the cell kernel of an n^dim micro mesh."""
     N = n**dim
+    if kind != POISSON and variant == ASSEMBLED:
+        return max(64, 32 * (-(-N // 32)))  # one thread per node
     if kind == POISSON:
-        nt = -(-N // 2)  # two nodes per thread
+        # four nodes per thread and several CTAs per SM beat two nodes per thread and one CTA
+        # (measured on B200, scripts/probe_occ.py: C3 12.2M -> 19.0M, C2 7.0M -> 11.6M points/s)
+        nt = -(-N // 4)
         nt = max(64, min(1024, 32 * (-(-nt // 32))))
         return nt
     nrhs = dim * (dim + 1) // 2
@@ -139,19 +161,36 @@ def _src_hash():
     return hsh.hexdigest()[:12]
 
 
-def kernel_key(prog: CoefficientProgram, n, threads):
-    return f"{'p' if prog.kind == POISSON else 'e'}{prog.dim}_n{n}_t{threads}_{prog.key}_{_src_hash()}"
+def default_min_blocks(dim, kind, n, threads):
+    """__launch_bounds__ minimum of resident CTAs per SM (caps registers per thread).  The Poisson
+    kernels are latency-bound (few PCG iterations, ~25 barriers per point): two or more CTAs per SM
+    hide it; 128 registers per thread still compile without spills."""
+    if kind != POISSON:
+        return 1
+    return max(1, min(8, 65536 // (threads * 128)))
 
 
-def kernel_defines(prog, n, threads, coeff_path):
-    return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}"]
+def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE):
+    return f"{'p' if prog.kind == POISSON else 'e'}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}_{prog.key}_{_src_hash()}"
 
 
-def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_log=True):
+def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE):
+    return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}",
+            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}"]  # fmt: skip
+
+
+def resolve(prog, n, threads=None, min_blocks=None, variant=None):
+    variant = default_variant(prog, n) if variant is None else variant
+    threads = threads or default_threads(prog.dim, prog.kind, n, variant)
+    min_blocks = min_blocks or default_min_blocks(prog.dim, prog.kind, n, threads)
+    return threads, min_blocks, variant
+
+
+def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_log=True, min_blocks=None, variant=None):
     """nvcc -cubin of the cell kernel for this coefficient program; returns the cubin path."""
-    threads = threads or default_threads(prog.dim, prog.kind, n)
+    threads, min_blocks, variant = resolve(prog, n, threads, min_blocks, variant)
     os.makedirs(KCACHE, exist_ok=True)
-    key = kernel_key(prog, n, threads)
+    key = kernel_key(prog, n, threads, min_blocks, variant)
     cubin = os.path.join(KCACHE, key + ".cubin")
     if os.path.exists(cubin) and not force:
         return cubin
@@ -160,7 +199,7 @@ def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_
         f.write(prog.source)
     tmp = cubin + f".tmp{os.getpid()}"
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I", CSRC,
-           *kernel_defines(prog, n, threads, coeff), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
+           *kernel_defines(prog, n, threads, coeff, min_blocks, variant), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
@@ -182,14 +221,15 @@ class CellSolver:
     h) and ``qw`` (nq,) normalised weights -- built by ``hommx_b200.micro.quadrature_table``.
     """
 
-    def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None):
+    def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None,
+                 min_blocks=None, variant=None):
         self.prog = prog
         self.dim, self.kind, self.n = prog.dim, prog.kind, int(n_micro)
         self.m = prog.n_rhs
         self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
         self._h = C.c_void_p()
         self.lib = load_library()
-        cubin = compile_kernel(prog, self.n, threads)
+        cubin = compile_kernel(prog, self.n, threads, min_blocks=min_blocks, variant=variant)
         with open(cubin, "rb") as f:
             image = f.read()
         self._image = C.create_string_buffer(image, len(image))

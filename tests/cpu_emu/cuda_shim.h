@@ -49,6 +49,16 @@ inline void barrier(int id, int count) {
 }
 inline void sync() { barrier(0, emu::g_cta->nthreads); }
 inline void group_sync(int id, int count) { barrier(id, count); }
+inline void warp_sync() { barrier(16 + emu::g_cta->cur / 32, 32); }
+inline double ld_stream(const double* p) { return *p; }
+inline void ld_stream_pair(const double* p, double& a, double& b) {
+  a = p[0];
+  b = p[1];
+}
+inline void st_pair(double* p, double a, double b) {
+  p[0] = a;
+  p[1] = b;
+}
 inline double* dyn_smem() { return emu::g_cta->smem; }
 inline double warp_sum(double v) {
   emu::Cta* c = emu::g_cta;

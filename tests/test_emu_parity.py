@@ -28,6 +28,24 @@ def test_cell_tensor_matches_oracle(case):
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max(), (case.name, it, res)
 
 
+ELAST = [c for c in LIGHT if c.kind == 1]
+
+
+@pytest.mark.parametrize("case", ELAST, ids=[c.name for c in ELAST])
+def test_matrix_free_elasticity_variant_matches_oracle(case):
+    """Small elasticity cells default to the assembled (L2-streamed) kernel; the matrix-free element
+    kernel (used for cells that do not fit) is checked on the same cases."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=0)
+    x = K.points(case, 2)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+
+
 @pytest.mark.parametrize("name", ["p2_fulltensor_strat_n9", "p3_fulltensor_shear_n5", "e2_hooke_sin_strat_n7", "e3_hooke_smooth_n4"])
 def test_local_matrix_matches_oracle(name):
     """Fused mode: macro cell vertices in, S_loc out (hmm.py:334-369 end to end)."""
