@@ -32,12 +32,12 @@ ELAST = [c for c in LIGHT if c.kind == 1]
 
 
 @pytest.mark.parametrize("case", ELAST, ids=[c.name for c in ELAST])
-def test_matrix_free_elasticity_variant_matches_oracle(case):
-    """Small elasticity cells default to the assembled (L2-streamed) kernel; the matrix-free element
-    kernel (used for cells that do not fit) is checked on the same cases."""
+def test_assembled_elasticity_variant_matches_oracle(case):
+    """The opt-in assembled (L2-streamed operator) elasticity kernel on the same cases as the default
+    matrix-free element kernel."""
     prog = K.program(case)
     qp, qw = K.tables(case, prog)
-    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=0)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=1)
     x = K.points(case, 2)
     Ah = s.cell_tensors(x)
     mic = K.oracle_cell(case, prog)

@@ -52,6 +52,24 @@ def test_local_matrix_matches_oracle(name):
     s.close()
 
 
+ELAST = [c for c in ALL if c.kind == 1]
+
+
+@pytest.mark.parametrize("case", ELAST, ids=[c.name for c in ELAST])
+def test_assembled_elasticity_variant_matches_oracle(case):
+    """The opt-in variant that assembles the micro operator into an L2-resident buffer."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=native.ASSEMBLED)
+    x = K.points(case, 3)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    s.close()
+
+
 def test_many_points_grid_stride():
     """More points than resident CTAs: every point is computed exactly once (persistent grid)."""
     case = K.BY_NAME["p2_smooth_n16_c1"]
