@@ -59,7 +59,7 @@ CELL_RTOL, CELL_ATOL = 1e-8, 1e-10
 SHRINK = 1
 
 
-def build_solver(wl, world, **kw):
+def build_solver(wl, world, collapse=False, **kw):
     import hommx_b200 as hx
     from hommx_b200 import mesh
     from hommx_b200 import ufl as pufl
@@ -74,8 +74,9 @@ def build_solver(wl, world, **kw):
     opts = {"ksp_rtol": CELL_RTOL, "ksp_atol": CELL_ATOL}
     cls = getattr(hx, w["cls"])
     if w["dtheta"]:
-        return cls(msh, A, f, mic, w["eps"], getattr(Cf, w["dtheta"])(pufl), petsc_options_cell_problem=opts, **kw)
-    return cls(msh, A, f, mic, w["eps"], petsc_options_cell_problem=opts, **kw)
+        return cls(msh, A, f, mic, w["eps"], getattr(Cf, w["dtheta"])(pufl), petsc_options_cell_problem=opts,
+                   collapse_invariant_axes=collapse, **kw)
+    return cls(msh, A, f, mic, w["eps"], petsc_options_cell_problem=opts, collapse_invariant_axes=collapse, **kw)
 
 
 def kernel_jobs():
@@ -87,7 +88,9 @@ def kernel_jobs():
     for w in WORKLOADS.values():
         A = getattr(Cf, w["coeff"])(pufl)
         Dt = getattr(Cf, w["dtheta"])(pufl) if w["dtheta"] else None
-        jobs.append((codegen.build_program(A, w["dim"], w["kind"], Dt), w["n"], None))
+        prog = codegen.build_program(A, w["dim"], w["kind"], Dt)
+        jobs.append((prog, w["n"], None))
+        jobs.append((prog, w["n"], None, False, True, None, None, True))  # axis-collapsed variant (other_workloads)
     return jobs
 
 
@@ -343,13 +346,14 @@ def run_ours(args, rank, world, local_rank):
     # secondary workloads (N=1 only, a few ms each): parity-test configs, reported for context
     other = {}
     if world == 1 and not args.no_extra:
-        for name in ("c2", "c3"):
-            if name == args.workload:
+        for name, collapse in (("c2", False), ("c3", False), ("c4", True), ("c3", True), ("c2", True)):
+            if name == args.workload and not collapse:
                 continue
+            key = name + ("_axis_collapsed" if collapse else "")
             try:
-                other[name] = quick_rate(name, local_rank)
+                other[key] = quick_rate(name, local_rank, collapse)
             except Exception as e:  # never lose the headline line
-                other[name] = {"error": str(e)[:200]}
+                other[key] = {"error": str(e)[:200]}
     # CPU baseline: bounded sample on the host cores
     cpu = None
     if not args.no_cpu:
@@ -360,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "macro_cells": n_total, "macro_cells_per_gpu": n_local,
-                   "macro_nnz": nnz, "cell_rtol": CELL_RTOL, "cell_atol": CELL_ATOL, "mean_pcg_iterations": mean_it,
+                   "macro_nnz": nnz, "axis_collapse": False, "cell_rtol": CELL_RTOL, "cell_atol": CELL_ATOL, "mean_pcg_iterations": mean_it,
                    "max_rel_residual": max_res, "macro_assembly_wall_ms": ms_per_step,
                    "l2": "flushed (256 MiB write) between timed steps", "parallelism": f"macro cells sharded over {world} GPU(s)"},
         "clocks": clocks, "gpu_launches": n_launch,
@@ -377,10 +381,10 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def quick_rate(name, device):
+def quick_rate(name, device, collapse=False):
     import torch
 
-    hmm = build_solver(name, 1, device=device)
+    hmm = build_solver(name, 1, collapse=collapse, device=device)
     hmm._ensure_solver()
     sol, d = hmm._solver, hmm._dev
     sol.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -394,7 +398,9 @@ def quick_rate(name, device):
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    return {"desc": WORKLOADS[name]["desc"], "macro_cells": n, "ms_per_step": best, "cell_solves_per_s": n / (best * 1e-3),
+    note = ("micro axes the coefficient does not depend on solved on one layer of cubes (exact symmetry reduction, "
+            "same A_hom to 1e-10; DESIGN.md 4)") if collapse else "full n^d micro cell"
+    return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n, "ms_per_step": best, "cell_solves_per_s": n / (best * 1e-3),
             "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
 
 

@@ -7,6 +7,7 @@ from .hmm import (  # noqa: F401
     LinearElasticityHMM,
     LinearElasticityStratifiedHMM,
     PoissonHMM,
+    PoissonPeriodicHMM,
     PoissonStratifiedHMM,
 )
 
@@ -15,6 +16,7 @@ __all__ = [
     "PoissonStratifiedHMM",
     "LinearElasticityHMM",
     "LinearElasticityStratifiedHMM",
+    "PoissonPeriodicHMM",
     "BaseHMM",
     "mesh",
     "fem",

@@ -60,29 +60,36 @@ HMX_HOSTDEV constexpr int sym_index(int D, int i, int j) {  // upper triangle, r
   return i <= j ? i * D - i * (i - 1) / 2 + (j - i) : j * D - j * (j - 1) / 2 + (i - j);
 }
 
-template <int D, int NM>
+// Periodic node grid.  COLL is a bit mask of COLLAPSED axes: when the coefficient does not depend
+// on y_a (CO::YDEP), operator and load vectors are invariant under translation along axis a (the
+// Kuhn mesh is too), so the correctors are constant along that axis and the cell problem is solved
+// EXACTLY on a single layer of cubes (extent 1, periodic onto itself) with the element volume
+// multiplied by the number of layers.  COLL = 0 is the full NM^D grid.
+template <int D, int NM, int COLL = 0>
 struct Grid {
-  static constexpr int N = ipow(NM, D);
+  HMX_HOSTDEV static constexpr int ext(int a) { return (a < D && !((COLL >> a) & 1)) ? NM : 1; }
+  static constexpr int N = ext(0) * ext(1) * ext(2);
+  static constexpr int NLAYERS = ipow(NM, popcount3(COLL & ((1 << D) - 1)));
   HMX_DEV static void decode(int i, int (&c)[3]) {
-    c[0] = i % NM;
-    c[1] = (i / NM) % NM;
-    c[2] = D == 3 ? i / (NM * NM) : 0;
+    c[0] = i % ext(0);
+    c[1] = (i / ext(0)) % ext(1);
+    c[2] = i / (ext(0) * ext(1));
   }
-  HMX_DEV static int up(int v) { return v + 1 == NM ? 0 : v + 1; }
-  HMX_DEV static int down(int v) { return v == 0 ? NM - 1 : v - 1; }
-  HMX_DEV static int index(int c0, int c1, int c2) { return D == 3 ? c0 + NM * (c1 + NM * c2) : c0 + NM * c1; }
+  HMX_DEV static int up(int v, int a) { return v + 1 >= ext(a) ? 0 : v + 1; }
+  HMX_DEV static int down(int v, int a) { return v == 0 ? ext(a) - 1 : v - 1; }
+  HMX_DEV static int index(int c0, int c1, int c2) { return c0 + ext(0) * (c1 + ext(1) * c2); }
   // node at c + mask (sign=+1) or c - mask (sign=-1); mask has one bit per axis
   template <int SIGN>
   HMX_DEV static int shifted(const int (&c)[3], int mask) {
     int s[3];
     HMX_UNROLL
-    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a]) : down(c[a])) : c[a];
+    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a], a) : down(c[a], a)) : c[a];
     return index(s[0], s[1], s[2]);
   }
   template <int SIGN>
   HMX_DEV static void shift_coords(const int (&c)[3], int mask, int (&s)[3]) {
     HMX_UNROLL
-    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a]) : down(c[a])) : c[a];
+    for (int a = 0; a < 3; ++a) s[a] = (a < D && ((mask >> a) & 1)) ? (SIGN > 0 ? up(c[a], a) : down(c[a], a)) : c[a];
   }
 };
 
@@ -92,10 +99,11 @@ struct Grid {
 // layout corner b of those cubes sits at stride-2/-2NM/-2NM^2 addresses (8-way bank conflicts for
 // n = 8, measured: 66 % of the shared-memory wavefronts of the first version were conflicts); in
 // this layout they are consecutive doubles.  For odd NM the classes are padded (decode -> valid).
-template <int D, int NM>
+template <int D, int NM, int COLL = 0>
 struct PGrid {
-  static constexpr int H = (NM + 1) / 2;
-  static constexpr int HC = ipow(H, D);
+  using G = Grid<D, NM, COLL>;
+  HMX_HOSTDEV static constexpr int H(int a) { return (G::ext(a) + 1) / 2; }
+  static constexpr int HC = H(0) * H(1) * H(2);
   static constexpr int NP = (1 << D) * HC;
   HMX_DEV static int index(const int (&c)[3]) {
     int cls = 0, idx = 0, s = 1;
@@ -103,7 +111,7 @@ struct PGrid {
     for (int a = 0; a < D; ++a) {
       cls |= (c[a] & 1) << a;
       idx += (c[a] >> 1) * s;
-      s *= H;
+      s *= H(a);
     }
     return cls * HC + idx;
   }
@@ -115,9 +123,9 @@ struct PGrid {
     for (int a = 0; a < 3; ++a) {
       c[a] = 0;
       if (a < D) {
-        c[a] = 2 * (r % H) + ((cls >> a) & 1);
-        r /= H;
-        ok = ok && c[a] < NM;
+        c[a] = 2 * (r % H(a)) + ((cls >> a) & 1);
+        r /= H(a);
+        ok = ok && c[a] < G::ext(a);
       }
     }
     return ok;

@@ -27,14 +27,14 @@
 
 namespace hmx {
 
-template <class CO, int NM, int NT>
+template <class CO, int NM, int NT, int COLL = 0>
 struct ElasticityLayout {
   static constexpr int D = CO::DIM;
   static constexpr int T = kuhn_ntypes<D>();
-  static constexpr int N = Grid<D, NM>::N;
+  static constexpr int N = Grid<D, NM, COLL>::N;
   static constexpr int NRHS = D * (D + 1) / 2;
   static constexpr int NV = NRHS;  // Voigt length
-  static constexpr int NP = PGrid<D, NM>::NP;  // node slots of the parity-major layout (>= N)
+  static constexpr int NP = PGrid<D, NM, COLL>::NP;  // node slots of the parity-major layout (>= N)
   static constexpr int NDOF = NP * D;
   static constexpr int TPR = NT / NRHS;  // threads per right-hand side
   static constexpr int NW = NT / 32;
@@ -43,7 +43,6 @@ struct ElasticityLayout {
   static constexpr int NA1 = NA > 0 ? NA : 1;
   static constexpr int NSYM = D * (D + 1) / 2;
   static constexpr int NRC = AtomIdx<D, NM, CO::YDEP, true>::NRC;
-  static constexpr int NCOL = (NM % 2 == 0) ? 2 : 3;  // colours per axis
   static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
   static constexpr int o_red = 0;                              // 2 buffers [NW][NREDV]
   static constexpr int o_stat = o_red + 2 * NW * NREDV;        // [NRHS][4] per right-hand side: its, rz, rz0
@@ -84,16 +83,18 @@ HMX_DEV void sym_inverse(const double* a, double* inv) {
 // One sweep over the cubes by the TPR threads of right-hand side q:  y += K p  (RHSMODE = false)
 // or  y += b_q  (RHSMODE = true: every element carries the unit strain -E_q; hmm.py:898-903).
 // Ms = sqrt(|e|) n M, so that e and sigma both carry sqrt(|e|) and the nodal forces the full |e|.
-template <class CO, int NM, int NT, bool RHSMODE>
+template <class CO, int NM, int NT, bool RHSMODE, int COLL = 0>
 HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
                               const double* s_p, double* s_y, int q, int l, double sqrtw) {
-  using L = ElasticityLayout<CO, NM, NT>;
-  using G = Grid<CO::DIM, NM>;
+  using L = ElasticityLayout<CO, NM, NT, COLL>;
+  using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
-  using PG = PGrid<CO::DIM, NM>;
-  constexpr int D = L::D, T = L::T, N = L::NP, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC, NCOL = L::NCOL;
-  constexpr int NC = 1 << D;    // corners
-  constexpr int HALF = NM / 2;  // size of colour classes 0 and 1 (class 2, odd n only: the last index)
+  using PG = PGrid<CO::DIM, NM, COLL>;
+  constexpr int D = L::D, T = L::T, N = L::NP, NV = L::NV, NA = L::NA, NA1 = L::NA1, NRC = L::NRC;
+  constexpr int NC = 1 << D;  // corners
+  // colours per axis: even extent -> 2 classes of ext/2 cubes; odd extent -> a third class holding the last index
+#define HMX_NCOL(a_) (G::ext(a_) % 2 == 0 ? 2 : 3)
+#define HMX_HALF(a_) (G::ext(a_) / 2)
 #define HMX_MZ(p_, ax_) ((CO::MZERO >> ((p_)*D + (ax_))) & 1u)
 
   // SLAB scheme (even NM, last-axis half-count divisible by the warps of the group): colours are
@@ -101,8 +102,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
   // indices.  Inside one last-axis parity the warps then write disjoint node planes, so the
   // colours of that parity only need the warp's own lock-step order (__syncwarp) and the group
   // barrier is needed twice per sweep instead of 2^D times.
-  constexpr bool SLAB = (NM % 2 == 0) && (HALF % L::WPR == 0);
-  constexpr int NCOLT = ipow(NCOL, D);
+  constexpr bool SLAB = COLL == 0 && (NM % 2 == 0) && ((NM / 2) % L::WPR == 0);
+  constexpr int NCOLT = (D > 0 ? HMX_NCOL(0) : 1) * (D > 1 ? HMX_NCOL(1) : 1) * (D > 2 ? HMX_NCOL(2) : 1);
+  constexpr int NCOL_LAST = HMX_NCOL(D - 1);
   const int wig = l >> 5, lig = l & 31;  // warp within the group, lane
   for (int col = 0; col < NCOLT; ++col) {
     int cls[3], cnt[3], total = 1;
@@ -111,9 +113,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
       int r = col;
       HMX_UNROLL
       for (int a = 0; a < 3; ++a) {
-        cls[a] = a < D ? r % NCOL : 0;
-        if (a < D) r /= NCOL;
-        cnt[a] = a < D ? (cls[a] == 2 ? 1 : HALF) : 1;
+        cls[a] = a < D ? r % HMX_NCOL(a) : 0;
+        if (a < D) r /= HMX_NCOL(a);
+        cnt[a] = a < D ? (cls[a] == 2 ? 1 : HMX_HALF(a)) : 1;
         total *= cnt[a];
       }
     }
@@ -128,9 +130,9 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         int r = k;
         HMX_UNROLL
         for (int a = 0; a < 3; ++a) {
-          const int idx = r % cnt[a];
-          r /= cnt[a];
-          o[a] = a < D ? (cls[a] == 2 ? NM - 1 : 2 * idx + cls[a]) : 0;
+          const int idx = cnt[a] > 0 ? r % cnt[a] : 0;
+          if (cnt[a] > 0) r /= cnt[a];
+          o[a] = a < D ? (cls[a] == 2 ? G::ext(a) - 1 : 2 * idx + cls[a]) : 0;
         }
       }
       int node[NC];
@@ -222,20 +224,23 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         HMX_UNROLL
         for (int j = 0; j < D; ++j) s_y[(q * D + j) * N + node[b]] += acc[b][j];
     }
-    if (SLAB && (col + 1) % (NCOLT / NCOL) != 0)
+    if (SLAB && (col + 1) % (NCOLT / NCOL_LAST) != 0)
       warp_sync();  // next colour has the same last-axis parity: only this warp's order matters
     else
       group_sync(1 + q, L::TPR);
   }
 #undef HMX_MZ
+#undef HMX_NCOL
+#undef HMX_HALF
 }
 
-template <class CO, int NM, int NT>
+template <class CO, int NM, int NT, int COLL = 0>
 HMX_DEV void elasticity_cell_body(const CellParams& P) {
-  using L = ElasticityLayout<CO, NM, NT>;
-  using G = Grid<CO::DIM, NM>;
+  static_assert((COLL & CO::YDEP) == 0, "only axes the coefficient does not depend on can be collapsed");
+  using L = ElasticityLayout<CO, NM, NT, COLL>;
+  using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
-  using PG = PGrid<CO::DIM, NM>;
+  using PG = PGrid<CO::DIM, NM, COLL>;
   // N counts node SLOTS of the parity-major layout; padding slots (odd NM) hold zeros in every vector
   // and in the preconditioner, so the vector loops need no validity test.
   constexpr int D = L::D, T = L::T, N = L::NP, NRHS = L::NRHS, NV = L::NV, NDOF = L::NDOF, TPR = L::TPR, NW = L::NW;
@@ -257,7 +262,8 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   const int q = t_id / TPR, l = t_id - q * TPR;
   const int lane = t_id & 31, warp = t_id >> 5;
   const double h = 1.0 / (double)NM;
-  const double vol = (D == 2 ? 0.5 * h * h : h * h * h / 6.0);
+  // |e| times the number of identical layers a collapsed grid stands for
+  const double vol = (D == 2 ? 0.5 * h * h : h * h * h / 6.0) * (double)G::NLAYERS;
   const double sqrtw = sqrt(vol);
   int red_flip = 0;
 
@@ -385,7 +391,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       for (int ww = 0; ww < WPR; ++ww) s += buf[q * WPR + ww];
       return s;
     };
-    elasticity_sweep<CO, NM, NT, true>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
+    elasticity_sweep<CO, NM, NT, true, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
     double rz, rz0;
     {
       double part = 0.0;
@@ -418,7 +424,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     const double tol2 = fmax(P.rtol * P.rtol * rz0, P.atol * P.atol);
     while (active && it < P.max_it) {
       ++it;
-      elasticity_sweep<CO, NM, NT, false>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
+      elasticity_sweep<CO, NM, NT, false, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -487,7 +493,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
-    elasticity_sweep<CO, NM, NT, true>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
+    elasticity_sweep<CO, NM, NT, true, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
     sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {
       double z[2 * NRHS];

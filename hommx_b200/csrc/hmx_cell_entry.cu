@@ -18,15 +18,19 @@
 #ifndef HMX_MINB
 #define HMX_MINB 1
 #endif
+#ifndef HMX_COLL
+#define HMX_COLL 0  // bit mask of collapsed micro axes (exact symmetry reduction, hmx_cell_common.cuh)
+#endif
 
 namespace {
 #if HMX_KIND == 0
-using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
 #elif HMX_VARIANT == 1
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #else
-using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
 #endif
+static_assert(HMX_VARIANT == 0 || HMX_COLL == 0, "the assembled variant has no collapsed form");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
 constexpr int kSmemBytes = Layout::total * 8;
 constexpr int kScratch = Layout::scratch_doubles;
@@ -35,11 +39,11 @@ constexpr int kScratch = Layout::scratch_doubles;
 #ifndef HMX_EMULATE
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #if HMX_KIND == 0
-  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
-  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #endif
 }
 // 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree
@@ -50,11 +54,11 @@ extern "C" __device__ const int hmx_info[8] = {kSmemBytes, HMX_NT,  Layout::NRHS
 static void emu_body(void* arg) {
   const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
 #if HMX_KIND == 0
-  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
-  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #endif
 }
 extern "C" void hmx_emu_info(int* out) {

@@ -24,11 +24,11 @@
 
 namespace hmx {
 
-template <class CO, int NM, int NT>
+template <class CO, int NM, int NT, int COLL = 0>
 struct PoissonLayout {
   static constexpr int D = CO::DIM;
   static constexpr int T = kuhn_ntypes<D>();
-  static constexpr int N = Grid<D, NM>::N;
+  static constexpr int N = Grid<D, NM, COLL>::N;
   static constexpr int NRHS = D;
   static constexpr int NH = (1 << D) - 1;  // stored (positive) stencil directions
   static constexpr int NW = NT / 32;
@@ -53,10 +53,11 @@ struct PoissonLayout {
   static constexpr int scratch_doubles = 0;
 };
 
-template <class CO, int NM, int NT>
+template <class CO, int NM, int NT, int COLL = 0>
 HMX_DEV void poisson_cell_body(const CellParams& P) {
-  using L = PoissonLayout<CO, NM, NT>;
-  using G = Grid<CO::DIM, NM>;
+  static_assert((COLL & CO::YDEP) == 0, "only axes the coefficient does not depend on can be collapsed");
+  using L = PoissonLayout<CO, NM, NT, COLL>;
+  using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
   constexpr int D = L::D, T = L::T, N = L::N, NRHS = L::NRHS, NH = L::NH, NW = L::NW;
   constexpr int NA = L::NA, NA1 = L::NA1, NPAIR = L::NPAIR, NSYM = L::NSYM, NRC = L::NRC;
@@ -77,7 +78,8 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
 
   const int t_id = tid();
   const double h = 1.0 / (double)NM;
-  const double vol = (D == 2 ? 0.5 : 1.0 / 6.0) * (D == 2 ? h * h : h * h * h);  // |e|
+  // |e| times the number of identical layers a collapsed grid stands for
+  const double vol = (D == 2 ? 0.5 : 1.0 / 6.0) * (D == 2 ? h * h : h * h * h) * (double)G::NLAYERS;
   int red_flip = 0;
 
   for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {

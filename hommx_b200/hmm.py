@@ -64,6 +64,7 @@ class BaseHMM:
         quadrature_rule=None,
         device=None,
         shard=True,
+        collapse_invariant_axes=True,
     ):
         self._logger = logging.getLogger(__name__)
         self._msh = as_simplex_mesh(msh)
@@ -123,6 +124,9 @@ class BaseHMM:
         self._A_values = np.zeros(self._pattern.nnz)
         self._A = None
         self._device = device
+        # exact symmetry reduction: micro axes the coefficient does not depend on are solved on one layer of
+        # cubes (csrc/hmx_cell_common.cuh, Grid<.., COLL>); False solves the full n^d cell
+        self._collapse = bool(collapse_invariant_axes)
         self._shard = bool(shard)  # False: assemble every macro cell on this GPU even if torch.distributed is up
         self._solver = None
         self._dev = None
@@ -162,7 +166,7 @@ class BaseHMM:
         self._device = int(dev)
         self._solver = native.CellSolver(
             self._program, self._structure.n, self._qp, self._qw, rtol=self._cell_rtol, atol=self._cell_atol,
-            max_it=self._cell_max_it, device=self._device,
+            max_it=self._cell_max_it, device=self._device, collapse=self._collapse,
         )  # fmt: skip
         tdev = torch.device("cuda", self._device)
         n_cells = self._msh.num_cells
@@ -329,3 +333,89 @@ class LinearElasticityStratifiedHMM(BaseHMM):
                  petsc_options_cell_problem=None, petsc_options_prefix="hommx_LinearElasticityHMM", **kw):  # fmt: skip
         super().__init__(msh, A, f, msh_micro, eps, petsc_options_global_solve, petsc_options_cell_problem,
                          petsc_options_prefix, Dtheta_transpose=Dtheta_transpose, **kw)  # fmt: skip
+
+
+# ----------------------------------------------------------------------------------------------
+class PoissonPeriodicHMM:
+    """Periodic homogenisation for scalar diffusion, ``A = A(y)`` (hmm.py:1070-1279): one cell
+    problem per direction gives the constant tensor ``A_hom`` (``compute_effective_tensor``,
+    hmm.py:1219-1245) -- the one-point special case of the HMM cell kernel -- followed by a
+    constant-coefficient macro problem (hmm.py:1247-1255).  No default boundary condition
+    (hmm.py:1132).  ``correctors`` are not returned by the cell kernel (gap)."""
+
+    def __init__(self, msh, A, f, msh_micro, eps, petsc_options_global_solve=None, petsc_options_cell_problem=None,
+                 petsc_options_prefix="hommx_periodicHMM", *, quadrature_rule=None, device=None):  # fmt: skip
+        self._logger = logging.getLogger(__name__)
+        self._msh = as_simplex_mesh(msh)
+        self._cell_mesh = as_simplex_mesh(msh_micro)
+        self._tdim = self._cell_mesh.dim
+        if self._tdim not in (2, 3):
+            raise ValueError("Only 2D and 3D periodic homogenization supported.")  # hmm.py:1098-1099
+        self._coeff, self._f, self._eps = A, f, eps
+        if petsc_options_cell_problem is None:
+            petsc_options_cell_problem = {"ksp_atol": 1e-12}  # hmm.py:1102-1104
+        self._petsc_options_cell_problem = dict(petsc_options_cell_problem)
+        self._petsc_options_global_solve = petsc_options_global_solve
+        self._V_macro = fem.FunctionSpace(self._msh, 1)
+        self._u = fem.Function(self._V_macro)
+        self._bcs = []
+        self._A_hom = None
+        # the HMM machinery with a coefficient that ignores the macro point
+        self._hmm = BaseHMM(self._msh, lambda x, y: A(y), f, self._cell_mesh, eps, petsc_options_global_solve,
+                            {"ksp_rtol": float(self._petsc_options_cell_problem.get("ksp_rtol", 1e-10)),
+                             "ksp_atol": float(self._petsc_options_cell_problem.get("ksp_atol", 1e-12)),
+                             "ksp_max_it": int(self._petsc_options_cell_problem.get("ksp_max_it", 10000))},
+                            petsc_options_prefix, quadrature_rule=quadrature_rule, device=device, shard=False)  # fmt: skip
+
+    @property
+    def function_space(self):
+        return self._V_macro
+
+    def set_boundary_conditions(self, bcs):
+        self._bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
+
+    def set_right_hand_side(self, f):
+        self._f = f
+
+    @property
+    def A_hom(self):
+        return self._A_hom
+
+    @property
+    def correctors(self):
+        raise NotImplementedError("the cell kernel reduces A_hom on chip and does not export the correctors")
+
+    def compute_effective_tensor(self):
+        """One GPU cell solve (all directions at once); returns the (d, d) tensor."""
+        self._A_hom = self._hmm.cell_tensors(np.zeros((1, 3)))[0]
+        return self._A_hom
+
+    def solve(self):
+        if self._A_hom is None:
+            self.compute_effective_tensor()
+        msh, d = self._msh, self._tdim
+        pat = self._hmm._pattern
+        vals = np.zeros(pat.nnz)
+        X = msh.x[:, :d]
+        for c, nodes in enumerate(msh.cells):  # constant-coefficient P1 stiffness (host, outside the hot path)
+            v = X[nodes]
+            J = (v[1:] - v[0]).T
+            Ji = np.linalg.inv(J)
+            G = np.concatenate([-Ji.sum(axis=0, keepdims=True), Ji], axis=0).T  # (d, d+1)
+            S = abs(np.linalg.det(J)) / (2 if d == 2 else 6) * (G.T @ self._A_hom.T @ G)
+            np.add.at(vals, pat.slot_map[c], S.ravel())
+        A = sp.csr_matrix((vals, pat.indices, pat.indptr), shape=(pat.n_dofs,) * 2)
+        self._A = A.copy()
+        b = fem.assemble_load(self._V_macro, self._f)
+        n = pat.n_dofs
+        for bc in self._bcs:
+            u_bc = np.zeros(n)
+            u_bc[bc.dofs] = bc.values
+            b = b - A @ u_bc
+            keep = np.ones(n)
+            keep[bc.dofs] = 0.0
+            Dk = sp.diags(keep)
+            A = (Dk @ A @ Dk + sp.diags(1.0 - keep)).tocsr()
+            b[bc.dofs] = bc.values
+        self._u.x.array[:] = spla.spsolve(A.tocsc(), b)
+        return self._u

@@ -133,9 +133,16 @@ def default_variant(prog, n):
     return ASSEMBLED if (fits and os.environ.get("HMX_ELASTICITY_VARIANT") == "assembled") else MATRIX_FREE
 
 
-def default_threads(dim, kind, n, variant=MATRIX_FREE):
-    """Threads per CTA for the cell kernel of an n^dim micro mesh."""
-    N = n**dim
+def collapse_mask(prog, collapse=True):
+    """Bit mask of the micro axes the coefficient does not depend on (they can be collapsed exactly)."""
+    if not collapse:
+        return 0
+    return ~prog.ydep & ((1 << prog.dim) - 1)
+
+
+def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
+    """Threads per CTA for the cell kernel of an n^dim micro mesh (minus its collapsed axes)."""
+    N = n ** (dim - bin(coll).count("1"))
     if kind != POISSON and variant == ASSEMBLED:
         return max(64, 32 * (-(-N // 32)))  # one thread per node
     if kind == POISSON:
@@ -145,7 +152,7 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE):
         nt = max(64, min(1024, 32 * (-(-nt // 32))))
         return nt
     nrhs = dim * (dim + 1) // 2
-    ncol = 2**dim
+    ncol = 2 ** (dim - bin(coll).count("1"))
     per = -(-N // ncol)  # cubes of one colour (even n)
     tpr = max(32, min(64, 32 * (-(-per // 32))))
     return tpr * nrhs
@@ -170,27 +177,30 @@ def default_min_blocks(dim, kind, n, threads):
     return max(1, min(8, 65536 // (threads * 128)))
 
 
-def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE):
-    return f"{'p' if prog.kind == POISSON else 'e'}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}_{prog.key}_{_src_hash()}"
+def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE, coll=0):
+    kind = "p" if prog.kind == POISSON else "e"
+    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}_{prog.key}_{_src_hash()}"
 
 
-def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE):
+def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE, coll=0):
     return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}",
-            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}"]  # fmt: skip
+            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}"]  # fmt: skip
 
 
-def resolve(prog, n, threads=None, min_blocks=None, variant=None):
+def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False):
     variant = default_variant(prog, n) if variant is None else variant
-    threads = threads or default_threads(prog.dim, prog.kind, n, variant)
+    coll = collapse_mask(prog, collapse) if variant == MATRIX_FREE else 0
+    threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll)
     min_blocks = min_blocks or default_min_blocks(prog.dim, prog.kind, n, threads)
-    return threads, min_blocks, variant
+    return threads, min_blocks, variant, coll
 
 
-def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_log=True, min_blocks=None, variant=None):
+def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_log=True, min_blocks=None, variant=None,
+                   collapse=False):
     """nvcc -cubin of the cell kernel for this coefficient program; returns the cubin path."""
-    threads, min_blocks, variant = resolve(prog, n, threads, min_blocks, variant)
+    threads, min_blocks, variant, coll = resolve(prog, n, threads, min_blocks, variant, collapse)
     os.makedirs(KCACHE, exist_ok=True)
-    key = kernel_key(prog, n, threads, min_blocks, variant)
+    key = kernel_key(prog, n, threads, min_blocks, variant, coll)
     cubin = os.path.join(KCACHE, key + ".cubin")
     if os.path.exists(cubin) and not force:
         return cubin
@@ -199,7 +209,7 @@ def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_
         f.write(prog.source)
     tmp = cubin + f".tmp{os.getpid()}"
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I", CSRC,
-           *kernel_defines(prog, n, threads, coeff, min_blocks, variant), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
+           *kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
@@ -222,14 +232,15 @@ class CellSolver:
     """
 
     def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None,
-                 min_blocks=None, variant=None):
+                 min_blocks=None, variant=None, collapse=False):
         self.prog = prog
         self.dim, self.kind, self.n = prog.dim, prog.kind, int(n_micro)
         self.m = prog.n_rhs
         self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
         self._h = C.c_void_p()
         self.lib = load_library()
-        cubin = compile_kernel(prog, self.n, threads, min_blocks=min_blocks, variant=variant)
+        cubin = compile_kernel(prog, self.n, threads, min_blocks=min_blocks, variant=variant, collapse=collapse)
+        self.collapse_mask = collapse_mask(prog, collapse)
         with open(cubin, "rb") as f:
             image = f.read()
         self._image = C.create_string_buffer(image, len(image))

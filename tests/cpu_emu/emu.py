@@ -26,21 +26,21 @@ class CellParams(C.Structure):
     ]  # fmt: skip
 
 
-def build(prog, n, threads=None, variant=None):
-    threads, min_blocks, variant = native.resolve(prog, n, threads, None, variant)
+def build(prog, n, threads=None, variant=None, collapse=False):
+    threads, min_blocks, variant, coll = native.resolve(prog, n, threads, None, variant, collapse)
     os.makedirs(BUILD, exist_ok=True)
     with open(os.path.join(HERE, "cuda_shim.h"), "rb") as f:
         shim = f.read()
     with open(os.path.join(HERE, "emu_runtime.h"), "rb") as f:
         shim += f.read()
-    key = native.kernel_key(prog, n, threads, min_blocks, variant) + "_" + hashlib.sha1(shim).hexdigest()[:8]
+    key = native.kernel_key(prog, n, threads, min_blocks, variant, coll) + "_" + hashlib.sha1(shim).hexdigest()[:8]
     so = os.path.join(BUILD, key + ".so")
     if not os.path.exists(so):
         coeff = os.path.join(BUILD, key + ".coeff.h")
         with open(coeff, "w") as f:
             f.write(prog.source)
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DHMX_EMULATE", "-I", HERE, "-I", native.CSRC,
-               *native.kernel_defines(prog, n, threads, coeff, min_blocks, variant), "-x", "c++", os.path.join(native.CSRC, "hmx_cell_entry.cu"),
+               *native.kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), "-x", "c++", os.path.join(native.CSRC, "hmx_cell_entry.cu"),
                "-o", so + ".tmp", "-lpthread"]  # fmt: skip
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
@@ -55,9 +55,9 @@ def build(prog, n, threads=None, variant=None):
 class EmuSolver:
     """Same call surface as hommx_b200.native.CellSolver's host entry points."""
 
-    def __init__(self, prog, n, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, threads=None, grid=4, variant=None):
+    def __init__(self, prog, n, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, threads=None, grid=4, variant=None, collapse=False):
         self.prog, self.n = prog, n
-        self.lib = build(prog, n, threads, variant)
+        self.lib = build(prog, n, threads, variant, collapse)
         info = (C.c_int * 8)()
         self.lib.hmx_emu_info(info)
         self.info = list(info)

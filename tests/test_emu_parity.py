@@ -62,3 +62,24 @@ def test_local_matrix_matches_oracle(name):
         So = ho.local_stiffness_from_tensor(Ao, verts, mic.kind)
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
         assert np.abs(S[k] - So).max() <= case.tol * np.abs(So).max()
+
+
+COLLAPSIBLE = ["p2_smooth_n15", "p2_laminate_wavy_n16", "p2_smooth_strat_n12", "p3_smooth_n8_c3", "p2_xonly_n7", "e2_hooke_sin_n6",
+               "e2_hooke_sin_strat_n7", "e3_hooke_const_n3", "e3_fibre_rot_n4"]  # fmt: skip
+
+
+@pytest.mark.parametrize("name", COLLAPSIBLE)
+def test_axis_collapse_is_exact(name):
+    """Coefficients that do not depend on y_a: the cell problem solved on one layer of cubes along a
+    (CO::YDEP / HMX_COLL) reproduces the full-grid oracle."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    assert prog.ydep != (1 << case.dim) - 1
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, collapse=True)
+    x = K.points(case, 2)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()

@@ -11,6 +11,7 @@ from hommx_b200 import (
     LinearElasticityHMM,
     LinearElasticityStratifiedHMM,
     PoissonHMM,
+    PoissonPeriodicHMM,
     PoissonStratifiedHMM,
     fem,
     mesh,
@@ -144,3 +145,20 @@ def test_elasticity_stratified_fibres_match_oracle():
     uo = ho.solve_dirichlet(Ao, b, dofs, np.zeros(len(dofs)))
     assert np.abs(u.x.array - uo).max() <= 1e-8 * np.abs(uo).max()
     assert s.cell_iterations.max() < 10000
+
+
+def test_hmm_equals_periodic_homogenisation():
+    """test/integration/test_integration_poisson.py:188-240: for A = A(y) PoissonHMM and PoissonPeriodicHMM
+    agree: macro matrices (Frobenius < 1e-8) and solutions (L2 < 1e-12 in the reference, with LU)."""
+    nm, n = 8, 8
+    A = Cf.periodic_only(pufl)
+    m = mesh.create_unit_square(nm, nm)
+    hmm = PoissonHMM(m, A, lambda x: 1.0, mesh.create_unit_square(n, n), 0.1 / n, petsc_options_cell_problem=TIGHT)
+    per = PoissonPeriodicHMM(m, lambda y: 2.0 + pufl.sin(2 * pufl.pi * y[0]), lambda x: 1.0, mesh.create_unit_square(n, n), 0.1 / n)
+    per.set_boundary_conditions(hmm._bcs)
+    u1, u2 = hmm.solve(), per.solve()
+    assert np.linalg.norm((hmm._A - per._A).toarray()) < 1e-8
+    assert np.abs(u1.x.array - u2.x.array).max() < 1e-12
+    mic = ho.MicroCell(omesh.create_unit_square(n, n), "poisson", 3)
+    Ao = ho.cell_tensor(mic, Cf.periodic_only(npufl), [0.0, 0.0, 0.0])
+    assert np.abs(per.A_hom - Ao).max() <= 1e-10 * np.abs(Ao).max()

@@ -70,6 +70,25 @@ def test_assembled_elasticity_variant_matches_oracle(case):
     s.close()
 
 
+COLLAPSIBLE = [c for c in ALL if K.program(c).ydep != (1 << c.dim) - 1]
+
+
+@pytest.mark.parametrize("case", COLLAPSIBLE, ids=[c.name for c in COLLAPSIBLE])
+def test_axis_collapse_is_exact(case):
+    """Axes the coefficient does not depend on collapsed to one layer of cubes: same A_hom as the full
+    n^d oracle (includes BASELINE configs 1-4: laminates and fibres)."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, collapse=True)
+    x = K.points(case, 3)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    s.close()
+
+
 def test_many_points_grid_stride():
     """More points than resident CTAs: every point is computed exactly once (persistent grid)."""
     case = K.BY_NAME["p2_smooth_n16_c1"]
