@@ -124,3 +124,29 @@ def test_errors_are_reported():
         rc = lib.hmx_create(C.byref(h), C.byref(d))
         assert rc == -3
         raise native.HmxError(lib.hmx_last_error(None).decode())
+
+
+def test_empty_and_degenerate_inputs():
+    """Edge cases at the C ABI: zero points / zero cells are no-ops, max_it is honoured and reported,
+    and a constant coefficient (no atoms, zero right-hand sides) needs no iteration."""
+    case = K.BY_NAME["p2_inclusion_n16"]
+    prog = K.program(case)
+    s = _solver(case, prog)
+    assert s.cell_tensors(np.zeros((0, 3))).shape == (0, 2, 2)
+    vals = s.assemble_macro(np.zeros((0, 3), dtype=np.int32), np.zeros((1, 3)), np.zeros(5, dtype=np.int64), np.zeros(0, dtype=np.int32))
+    assert vals.shape == (4,) and np.all(vals == 0.0)
+    x = K.points(case, 3)
+    s.set_tolerances(1e-12, 1e-14, 5)
+    A5, it, res = s.cell_tensors(x, return_stats=True)
+    assert np.all(it == 5) and np.all(res > 1e-6)  # stopped early, residual reported, no exception
+    s.set_tolerances(1e-10, 1e-12, 10000)
+    A, it, res = s.cell_tensors(x, return_stats=True)
+    assert np.all(it < 10000) and np.all(res <= 1e-10) and np.abs(A - A5).max() > 0
+    s.close()
+    case = K.BY_NAME["p2_xonly_n7"]
+    s = _solver(case, K.program(case))
+    A, it, res = s.cell_tensors(K.points(case, 4), return_stats=True)
+    assert np.all(it == 0) and np.all(res == 0.0)
+    s.close()
+    with pytest.raises(ValueError):
+        native.CellSolver(K.program(case), 7, np.zeros((2, 1, 3)), np.ones(1))  # wrong quadrature table shape
