@@ -37,22 +37,29 @@ struct ElasticityLayout {
   static constexpr int NP = PGrid<D, NM, COLL>::NP;  // node slots of the parity-major layout (>= N)
   static constexpr int NDOF = NP * D;
   static constexpr int TPR = NT / NRHS;  // threads per right-hand side
+  // small (e.g. axis-collapsed) cells have fewer cubes per colour than a warp has lanes: then a
+  // right-hand side gets a 16-/8-lane SEGMENT of a warp, the warp is the synchronisation group,
+  // reductions are segmented shuffles and the right-hand sides sharing a warp iterate together
+  static constexpr bool SUBW = TPR < 32;
+  static constexpr int TPG = SUBW ? 32 : TPR;  // threads per synchronisation group
   static constexpr int NW = NT / 32;
-  static constexpr int WPR = TPR / 32;  // warps per right-hand side
+  static constexpr int WPR = SUBW ? 1 : TPR / 32;  // warps per right-hand side
   static constexpr int NA = CO::NATOMS;
   static constexpr int NA1 = NA > 0 ? NA : 1;
   static constexpr int NSYM = D * (D + 1) / 2;
   static constexpr int NRC = AtomIdx<D, NM, CO::YDEP, true>::NRC;
   static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
   static constexpr int o_red = 0;                              // 2 buffers [NW][NREDV]
-  static constexpr int o_stat = o_red + 2 * NW * NREDV;        // [NRHS][4] per right-hand side: its, rz, rz0
+  static constexpr int NSLOT = NW > NRHS * WPR ? NW : NRHS * WPR;
+  static constexpr int o_stat = o_red + 2 * NSLOT * NREDV;     // [NRHS][4] per right-hand side: its, rz, rz0
   static constexpr int o_atoms = o_stat + 4 * NRHS;            // [NA][T][NRC]
   static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][NP] inverse diagonal blocks
   static constexpr int o_p = o_dinv + NSYM * NP;               // [NRHS][D][NP]
   static constexpr int o_y = o_p + NRHS * NDOF;                // [NRHS][D][N]
   static constexpr int total = o_y + NRHS * NDOF;
   static constexpr int scratch_doubles = 2 * NRHS * NDOF;      // x and r per CTA
-  static_assert(NT % NRHS == 0 && TPR % 32 == 0, "block size must be NRHS * (multiple of 32)");
+  static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
+                "block size must be NRHS * (a multiple or a divisor of 32)");
 };
 
 // inverse of a symmetric DxD matrix given by its upper triangle (row major)
@@ -102,7 +109,7 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
   // indices.  Inside one last-axis parity the warps then write disjoint node planes, so the
   // colours of that parity only need the warp's own lock-step order (__syncwarp) and the group
   // barrier is needed twice per sweep instead of 2^D times.
-  constexpr bool SLAB = COLL == 0 && (NM % 2 == 0) && ((NM / 2) % L::WPR == 0);
+  constexpr bool SLAB = !L::SUBW && COLL == 0 && (NM % 2 == 0) && ((NM / 2) % L::WPR == 0);
   constexpr int NCOLT = (D > 0 ? HMX_NCOL(0) : 1) * (D > 1 ? HMX_NCOL(1) : 1) * (D > 2 ? HMX_NCOL(2) : 1);
   constexpr int NCOL_LAST = HMX_NCOL(D - 1);
   const int wig = l >> 5, lig = l & 31;  // warp within the group, lane
@@ -226,6 +233,8 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
     }
     if (SLAB && (col + 1) % (NCOLT / NCOL_LAST) != 0)
       warp_sync();  // next colour has the same last-axis parity: only this warp's order matters
+    else if (L::SUBW)
+      warp_sync();  // the group is the warp
     else
       group_sync(1 + q, L::TPR);
   }
@@ -314,7 +323,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         HMX_UNROLL
         for (int k = 0; k < NA; ++k) smean[k] += s_atoms[k * T * NRC + idx];
       }
-      block_sum<NA1, NW>(smean, s_red + (red_flip ^= 1) * NW * L::NREDV);
+      block_sum<NA1, NW>(smean, s_red + (red_flip ^= 1) * L::NSLOT * L::NREDV);
       HMX_UNROLL
       for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * ipow(NM, AI::NDEP));  // padding slots hold 0
     }
@@ -382,14 +391,21 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     // ---- 3./4. one PCG per right-hand side, each group on its own named barrier ----
     // group-wide sum of one value per thread; buffers alternate so no trailing barrier is needed
     auto group_sum = [&](double v) {
+      if (L::SUBW) return seg_sum(v, TPR);  // the right-hand side owns a segment of one warp
       v = warp_sum(v);
-      double* buf = s_red + (red_flip ^= 1) * NW * L::NREDV;
+      double* buf = s_red + (red_flip ^= 1) * L::NSLOT * L::NREDV;
       if (lane == 0) buf[warp] = v;
       group_sync(1 + q, TPR);
       double s = 0.0;
       HMX_UNROLL
       for (int ww = 0; ww < WPR; ++ww) s += buf[q * WPR + ww];
       return s;
+    };
+    auto group_barrier = [&]() {
+      if (L::SUBW)
+        warp_sync();
+      else
+        group_sync(1 + q, TPR);
     };
     elasticity_sweep<CO, NM, NT, true, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
     double rz, rz0;
@@ -418,12 +434,15 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       rz = rz0 = group_sum(part);  // its barrier also publishes p and the zeroed y
+      if (L::SUBW) warp_sync();    // (segmented shuffles carry no memory ordering)
     }
     int it = 0;
     bool active = rz0 > P.atol * P.atol;
     const double tol2 = fmax(P.rtol * P.rtol * rz0, P.atol * P.atol);
-    while (active && it < P.max_it) {
-      ++it;
+    // SUBW: the right-hand sides sharing a warp loop together (the converged ones only keep y clean)
+    while (L::SUBW ? warp_any(active && it < P.max_it) : (active && it < P.max_it)) {
+      const bool mine = active && it < P.max_it;
+      if (mine) ++it;
       elasticity_sweep<CO, NM, NT, false, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
       double part = 0.0;
       HMX_UNROLL
@@ -435,7 +454,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       const double pAp = group_sum(part);
-      const double alpha = pAp > 0.0 ? rz / pAp : 0.0;
+      const double alpha = (mine && pAp > 0.0) ? rz / pAp : 0.0;
       part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -447,9 +466,12 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
             const int a = (q * D + c) * N + i;
             const double yv = s_y[a];
             s_y[a] = 0.0;
-            g_x[a] += alpha * s_p[a];
-            r[c] = g_r[a] - alpha * yv;
-            g_r[a] = r[c];
+            r[c] = g_r[a];
+            if (mine) {
+              g_x[a] += alpha * s_p[a];
+              r[c] -= alpha * yv;
+              g_r[a] = r[c];
+            }
           }
           HMX_UNROLL
           for (int c = 0; c < D; ++c) {
@@ -461,11 +483,12 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       const double rz_new = group_sum(part);
-      const double beta = rz_new / rz;
-      rz = rz_new;
-      if (!(rz_new > tol2)) {
-        active = false;
-      } else {
+      const double beta = mine ? rz_new / rz : 0.0;
+      if (mine) {
+        rz = rz_new;
+        if (!(rz_new > tol2)) active = false;
+      }
+      if (mine && active) {
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j) {
           const int i = l + j * TPR;
@@ -483,8 +506,8 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
             }
           }
         }
-        group_sync(1 + q, TPR);
       }
+      if (L::SUBW || active) group_barrier();  // publish p (and the zeroed y) to the group
     }
     if (l == 0) {
       s_stat[4 * q + 0] = (double)it;
@@ -515,14 +538,15 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       HMX_UNROLL
-      for (int k = 0; k < 2 * NRHS; ++k) z[k] = warp_sum(z[k]);
+      for (int k = 0; k < 2 * NRHS; ++k) z[k] = L::SUBW ? seg_sum(z[k], TPR) : warp_sum(z[k]);
       // the groups did different numbers of reductions: after the barrier above every thread
-      // restarts from the same buffer parity
+      // restarts from the same buffer parity.  One slot per (right-hand side, warp of that side).
       red_flip = 0;
       double* buf = s_red;
-      if (lane == 0) {
+      if (L::SUBW ? l == 0 : lane == 0) {
+        const int slot = L::SUBW ? q : warp;  // non-SUBW: warp = q * WPR + (warp within the side)
         HMX_UNROLL
-        for (int k = 0; k < 2 * NRHS; ++k) buf[warp * L::NREDV + k] = z[k];
+        for (int k = 0; k < 2 * NRHS; ++k) buf[slot * L::NREDV + k] = z[k];
       }
       sync();
       if (t_id == 0) {

@@ -45,6 +45,12 @@ HMX_DEV double warp_sum(double v) {
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
+// sum over aligned segments of `width` lanes (width = 1,2,4,8,16,32); every lane of the warp calls it
+HMX_DEV double seg_sum(double v, int width) {
+  for (int m = width >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  return v;
+}
+HMX_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 HMX_DEV double warp_max(double v) {
 #pragma unroll

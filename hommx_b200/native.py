@@ -154,6 +154,8 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
     nrhs = dim * (dim + 1) // 2
     ncol = 2 ** (dim - bin(coll).count("1"))
     per = -(-N // ncol)  # cubes of one colour (even n)
+    if per <= 16 and nrhs % 2 == 0:
+        return 16 * nrhs  # two right-hand sides share a warp (ElasticityLayout::SUBW)
     tpr = max(32, min(64, 32 * (-(-per // 32))))
     return tpr * nrhs
 

@@ -77,6 +77,33 @@ inline double warp_sum(double v) {
   }
   return t[me & 31];
 }
+inline double seg_sum(double v, int width) {
+  emu::Cta* c = emu::g_cta;
+  const int me = c->cur, par = c->wpar[me];
+  c->wbuf[par * c->nthreads + me] = v;
+  c->wpar[me] = par ^ 1;
+  barrier(16 + me / 32, 32);
+  const int w0 = (me / 32) * 32;
+  double t[32];
+  for (int l = 0; l < 32; ++l) t[l] = c->wbuf[par * c->nthreads + w0 + l];
+  for (int m = width >> 1; m > 0; m >>= 1) {
+    double u[32];
+    for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ m];
+    for (int l = 0; l < 32; ++l) t[l] = u[l];
+  }
+  return t[me & 31];
+}
+inline bool warp_any(bool p) {
+  emu::Cta* c = emu::g_cta;
+  const int me = c->cur, par = c->wpar[me];
+  c->wbuf[par * c->nthreads + me] = p ? 1.0 : 0.0;
+  c->wpar[me] = par ^ 1;
+  barrier(16 + me / 32, 32);
+  const int w0 = (me / 32) * 32;
+  bool any = false;
+  for (int l = 0; l < 32; ++l) any = any || c->wbuf[par * c->nthreads + w0 + l] != 0.0;
+  return any;
+}
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline double warp_max(double v) {
   emu::Cta* c = emu::g_cta;
