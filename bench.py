@@ -339,21 +339,23 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    # secondary workloads (N=1 only, a few ms each): parity-test configs, reported for context
+    # secondary workloads: parity-test configs and the axis-collapsed form, reported for context.
+    # At N > 1 only the collapsed headline config is repeated (every rank takes part).
     other = {}
-    if world == 1 and not args.no_extra:
-        for name, collapse in (("c2", False), ("c3", False), ("c4", True), ("c3", True), ("c2", True)):
+    if not args.no_extra:
+        todo = (("c2", False), ("c3", False), ("c4", True), ("c3", True), ("c2", True)) if world == 1 else ((args.workload, True),)
+        for name, collapse in todo:
             if name == args.workload and not collapse:
                 continue
             key = name + ("_axis_collapsed" if collapse else "")
             try:
-                other[key] = quick_rate(name, local_rank, collapse)
+                other[key] = quick_rate(name, local_rank, collapse, world)
             except Exception as e:  # never lose the headline line
                 other[key] = {"error": str(e)[:200]}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # CPU baseline: bounded sample on the host cores
     cpu = None
     if not args.no_cpu:
@@ -381,10 +383,11 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def quick_rate(name, device, collapse=False):
+def quick_rate(name, device, collapse=False, world=1):
     import torch
+    import torch.distributed as dist
 
-    hmm = build_solver(name, 1, collapse=collapse, device=device)
+    hmm = build_solver(name, world, collapse=collapse, device=device)
     hmm._ensure_solver()
     sol, d = hmm._solver, hmm._dev
     sol.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -395,13 +398,20 @@ def quick_rate(name, device, collapse=False):
         e0.record()
         sol.assemble_macro_dev(n, d["cells"], hmm._msh.num_nodes, d["xyz"], hmm._pattern.nnz, d["ptr"], d["src"], d["vals"], d["S"],
                                d["it"], d["res"])  # fmt: skip
+        if world > 1:
+            hmm._halo_sum()
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
+    if world > 1:
+        t = torch.tensor([best], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = t.item()
+    n_all = hmm._msh.num_cells
     note = ("micro axes the coefficient does not depend on solved on one layer of cubes (exact symmetry reduction, "
             "same A_hom to 1e-10; DESIGN.md 4)") if collapse else "full n^d micro cell"
-    return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n, "ms_per_step": best, "cell_solves_per_s": n / (best * 1e-3),
-            "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
+    return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n_all, "n_gpus": world, "ms_per_step": best,
+            "cell_solves_per_s": n_all / (best * 1e-3), "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
 
 
 def main():
