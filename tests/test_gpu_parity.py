@@ -150,3 +150,23 @@ def test_empty_and_degenerate_inputs():
     s.close()
     with pytest.raises(ValueError):
         native.CellSolver(K.program(case), 7, np.zeros((2, 1, 3)), np.ones(1))  # wrong quadrature table shape
+
+
+@pytest.mark.parametrize("name,kw", [("p2_inclusion_n16", {}), ("p3_fulltensor_n6", {}), ("e3_fibre_rot_n8_c4", {}),
+                                     ("e3_fibre_rot_n4", {"collapse": True}), ("e2_hooke_sin_n6", {}),
+                                     ("e3_fibre_rot_n4", {"variant": 1})])  # fmt: skip
+def test_results_are_bitwise_reproducible(name, kw):
+    """No atomics on the data path, fixed reduction orders, colour-ordered scatter: repeated runs and
+    different grid sizes give bit-identical A_hom (compute-sanitizer is closed on this pool; a data race in
+    the colouring / named-barrier logic would show up here as run-to-run differences)."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-9, **kw)
+    x = K.points(case, 300 if not case.heavy else 200, seed=11)
+    ref = s.cell_tensors(x)
+    for grid in (0, 7, 148):
+        s.set_grid(grid)
+        for _ in range(2):
+            assert np.array_equal(s.cell_tensors(x), ref)
+    s.close()
