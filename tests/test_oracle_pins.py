@@ -205,3 +205,30 @@ def test_constant_hooke_equals_plain_fem():
         dofs = ho.unroll_dofs(nodes, 3)
         Kf[np.ix_(dofs, dofs)] += S
     assert np.linalg.norm(K - Kf) / np.linalg.norm(Kf) < 1e-12
+
+
+def test_analytic_example_1_discrete_convergence():
+    """SURVEY.md 8c.1 (independent survey computation): the discrete A_hom[0,0] of
+    A = 1/(2+cos 2 pi y0) converges like O(h^2) to 1/2; n = 60 gives 0.500061199."""
+    mic = ho.MicroCell(meshes.create_unit_square(60, 60), "poisson", 3)
+    Ah = ho.cell_tensor(mic, C.analytic1(ufl), [0.1, 0.9, 0.0])
+    assert abs(Ah[0, 0] - 0.500061199) < 2e-9
+    assert abs(Ah[1, 1] - 1 / math.sqrt(3)) < 1e-9
+
+
+def test_hmm_equals_periodic_class_formula():
+    """BasePeriodicHMM (hmm.py:1199-1245, 1274-1279): A_hom[p,q] = 1/|Y| int A (e_q + grad chi_q) . e_p --
+    the non-symmetrised formula of the periodic class -- equals the oracle's energy form."""
+    mic = ho.MicroCell(meshes.create_unit_square(12, 12), "poisson", 3)
+    A = C.full_tensor_2d(ufl)
+    x = np.array([0.3, 0.7, 0.0])
+    Ah, chis = ho.cell_tensor(mic, A, x, return_correctors=True)
+    Abar = mic.element_coefficient(A, x)
+    _, B = mic.assemble(Abar, np.eye(2))
+    ne = len(mic.vol)
+    for q in range(2):
+        tot = np.broadcast_to(np.eye(2)[q], (ne, 2)) + mic.field_of(B, chis[q])
+        for p in range(2):
+            flux = np.einsum("eij,ej->ei", Abar, tot)  # A (e_q + grad chi_q) per element
+            val = float(np.einsum("e,ei->", mic.vol, flux * np.eye(2)[p]))
+            assert abs(val / mic.Y - Ah[p, q]) < 1e-12
