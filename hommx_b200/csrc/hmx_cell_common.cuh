@@ -28,6 +28,7 @@ struct CellParams {
   const double* qp;        // [T][nq][D] quadrature points, cube-local, in units of h
   const double* qw;        // [nq] weights normalised to sum 1
   double* scratch;         // per-CTA global scratch (elasticity: corrector vectors)
+  double* chi;             // [n_pts][n_rhs][bs][N_grid] correctors on the (possibly collapsed) periodic grid, or nullptr
   unsigned long long* work;  // device counter += sum over right-hand sides of PCG iterations (nullptr: off)
   int nq;
   int max_it;

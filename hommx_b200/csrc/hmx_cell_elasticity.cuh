@@ -549,6 +549,15 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         for (int k = 0; k < 2 * NRHS; ++k) buf[slot * L::NREDV + k] = z[k];
       }
       sync();
+      if (P.chi != nullptr) {  // correctors in natural node order: [q][component][node]
+        constexpr int NN = G::N;
+        for (int i = t_id; i < N; i += NT) {
+          int c[3];
+          if (!PG::decode(i, c)) continue;
+          const int nat = G::index(c[0], c[1], c[2]);
+          for (int k = 0; k < NRHS * D; ++k) P.chi[((size_t)pt * NRHS * D + k) * NN + nat] = g_x[k * N + i];
+        }
+      }
       if (t_id == 0) {
         double Ah[NRHS * NRHS];
         for (int qq = 0; qq < NRHS; ++qq) {

@@ -406,6 +406,9 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q) Ah[p * NRHS + q] = -zz[q] - zz[NRHS + q];
       }
+      if (P.chi != nullptr && own) {
+        for (int k = 0; k < NVEC; ++k) P.chi[((size_t)pt * NVEC + k) * N + i] = g_x[k * N + i];
+      }
       if (i == 0) {
         for (int q = 0; q < NRHS; ++q) {
           double e[NV], sg[NV];

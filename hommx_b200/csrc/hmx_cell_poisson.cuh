@@ -383,6 +383,16 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
             z[NRHS * NRHS + p * NRHS + q] += xq[j][p] * rq[j][q];
           }
       block_sum<2 * NRHS * NRHS, NW>(z, s_red + (red_flip ^= 1) * NW * L::NRED);
+      if (P.chi != nullptr) {  // correctors (BasePeriodicHMM.correctors, hmm.py:1211-1213), natural node order
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = t_id + j * NT;
+          if (i < N) {
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) P.chi[((size_t)pt * NRHS + q) * N + i] = xq[j][q];
+          }
+        }
+      }
       if (t_id == 0) {
         double Ah[NRHS * NRHS];
         HMX_UNROLL

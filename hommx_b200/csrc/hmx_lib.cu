@@ -189,7 +189,7 @@ int grid_1d(long long n, int threads, int sms) {
 }
 
 int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_nodes, const double* node_xyz,
-                double* A_hom, double* S_loc, int* iters, double* resid) {
+                double* A_hom, double* S_loc, int* iters, double* resid, double* chi = nullptr) {
   if (n_pts == 0) return HMX_OK;
   const int per_sm = std::max(1, h->info[5]);
   const int sms = h->info[6];
@@ -210,6 +210,7 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
   P.qp = h->qp.as<double>();
   P.qw = h->qw.as<double>();
   P.scratch = h->scratch.as<double>();
+  P.chi = chi;
   P.work = h->work.as<unsigned long long>();
   P.nq = h->nq;
   P.max_it = h->max_it;
@@ -414,6 +415,13 @@ int hmx_cell_tensors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A
   if (n_pts < 0 || (n_pts > 0 && (!x_pts || !A_hom))) return fail(h, HMX_ERR_ARG, "hmx_cell_tensors: null buffer");
   HMX_CUDA(h, cudaSetDevice(h->device));
   return launch_cell(h, n_pts, x_pts, nullptr, nullptr, A_hom, nullptr, iters, resid);
+}
+
+int hmx_cell_correctors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, double* chi) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_pts < 0 || (n_pts > 0 && (!x_pts || !chi))) return fail(h, HMX_ERR_ARG, "hmx_cell_correctors: null buffer");
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  return launch_cell(h, n_pts, x_pts, nullptr, nullptr, A_hom, nullptr, nullptr, nullptr, chi);
 }
 
 int hmx_cell_tensors(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid) {

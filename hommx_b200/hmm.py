@@ -360,6 +360,7 @@ class PoissonPeriodicHMM:
         self._u = fem.Function(self._V_macro)
         self._bcs = []
         self._A_hom = None
+        self._correctors = None
         # the HMM machinery with a coefficient that ignores the macro point
         self._hmm = BaseHMM(self._msh, lambda x, y: A(y), f, self._cell_mesh, eps, petsc_options_global_solve,
                             {"ksp_rtol": float(self._petsc_options_cell_problem.get("ksp_rtol", 1e-10)),
@@ -383,11 +384,26 @@ class PoissonPeriodicHMM:
 
     @property
     def correctors(self):
-        raise NotImplementedError("the cell kernel reduces A_hom on chip and does not export the correctors")
+        """One ``fem.Function`` on the micro mesh per direction (hmm.py:1211-1213), slaves of the periodic
+        constraint filled with their master's value; each is defined up to an additive constant."""
+        if self._correctors is None:
+            self.compute_effective_tensor()
+        return self._correctors
 
     def compute_effective_tensor(self):
         """One GPU cell solve (all directions at once); returns the (d, d) tensor."""
-        self._A_hom = self._hmm.cell_tensors(np.zeros((1, 3)))[0]
+        self._hmm._ensure_solver()
+        A, chi = self._hmm._solver.cell_correctors(np.zeros((1, 3)))
+        self._A_hom = A[0]
+        n, d = self._hmm._structure.n, self._tdim
+        ij = np.rint(self._cell_mesh.x[:, :d] * n).astype(np.int64) % n  # vertex -> periodic grid index
+        idx = tuple(ij[:, a] for a in reversed(range(d)))  # grid arrays are (z, y, x)
+        V = fem.FunctionSpace(self._cell_mesh, 1)
+        self._correctors = []
+        for q in range(d):
+            fn = fem.Function(V)
+            fn.x.array[:] = chi[0, q, 0][idx]
+            self._correctors.append(fn)
         return self._A_hom
 
     def solve(self):

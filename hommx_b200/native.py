@@ -86,6 +86,7 @@ SYMBOLS = {
     "hmx_kernel_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hmx_cell_tensors": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_cell_tensors_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_cell_correctors_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_assemble_macro": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_assemble_macro_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
@@ -336,6 +337,24 @@ class CellSolver:
     def cell_tensors_dev(self, n_pts, x_pts, A_hom, iters=None, resid=None):
         dp = self._dp
         self._check(self.lib.hmx_cell_tensors_dev(self._h, int(n_pts), dp(x_pts), dp(A_hom), dp(iters), dp(resid)))
+
+    def cell_correctors(self, x_pts):
+        """(A_hom (n, m, m), chi (n, n_rhs, bs, *grid)) with the grid in (z, y, x) order; collapsed axes are
+        broadcast back to the full n^d periodic grid."""
+        import torch
+
+        x = np.ascontiguousarray(np.asarray(x_pts, dtype=np.float64).reshape(-1, 3))
+        n, d = len(x), self.dim
+        bs = 1 if self.kind == POISSON else d
+        shape = [1 if (self.collapse_mask >> a) & 1 else self.n for a in range(d)]
+        dev = torch.device("cuda", torch.cuda.current_device())
+        xd = torch.as_tensor(x, device=dev)
+        A = torch.empty((n, self.m, self.m), dtype=torch.float64, device=dev)
+        chi = torch.zeros((n, self.m, bs) + tuple(reversed(shape)), dtype=torch.float64, device=dev)
+        self._check(self.lib.hmx_cell_correctors_dev(self._h, n, self._dp(xd), self._dp(A), self._dp(chi)))
+        self.sync()
+        full = (n, self.m, bs) + (self.n,) * d
+        return A.cpu().numpy(), np.broadcast_to(chi.cpu().numpy(), full).copy()
 
     def assemble_macro_dev(self, n_cells, cell_nodes, n_nodes, node_xyz, nnz, gather_ptr, gather_src, csr_vals, S_loc=None,
                            iters=None, resid=None):

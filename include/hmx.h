@@ -80,6 +80,12 @@ int hmx_kernel_info(const hmx_t* h, int32_t info[8]);
 int hmx_cell_tensors(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid);
 int hmx_cell_tensors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid);
 
+/* Same solve, additionally returning the correctors chi_q (BasePeriodicHMM.correctors, hmm.py:1211-1213):
+ * chi [n_pts][n_rhs][bs][N_grid] nodal values on the periodic micro grid in natural node order (x fastest;
+ * collapsed axes have extent 1), defined up to an additive constant per component.  A_hom may be NULL.
+ * Device pointers. */
+int hmx_cell_correctors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, double* chi);
+
 /* Macro stiffness assembly: replaces BaseHMM._assemble_stiffness (hmm.py:298-332) for the
  * `n_cells` macro cells given (a rank's owned cells, hmm.py:307).
  *   cell_nodes [n_cells][dim+1]  macro vertex ids (geometry dofmap)

@@ -21,7 +21,7 @@ class CellParams(C.Structure):
     _fields_ = [
         ("n_pts", C.c_int64), ("x_pts", C.c_void_p), ("cell_nodes", C.c_void_p), ("node_xyz", C.c_void_p),
         ("A_hom", C.c_void_p), ("S_loc", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p),
-        ("qp", C.c_void_p), ("qw", C.c_void_p), ("scratch", C.c_void_p), ("work", C.c_void_p),
+        ("qp", C.c_void_p), ("qw", C.c_void_p), ("scratch", C.c_void_p), ("chi", C.c_void_p), ("work", C.c_void_p),
         ("nq", C.c_int32), ("max_it", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
     ]  # fmt: skip
 
@@ -58,6 +58,7 @@ class EmuSolver:
     def __init__(self, prog, n, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, threads=None, grid=4, variant=None, collapse=False):
         self.prog, self.n = prog, n
         self.lib = build(prog, n, threads, variant, collapse)
+        self.collapse = collapse
         info = (C.c_int * 8)()
         self.lib.hmx_emu_info(info)
         self.info = list(info)
@@ -85,6 +86,20 @@ class EmuSolver:
         P.n_pts, P.x_pts, P.A_hom, P.iters, P.resid = n, x.ctypes.data, A.ctypes.data, it.ctypes.data, res.ctypes.data
         self._launch(P, n)
         return (A, it, res) if return_stats else A
+
+    def correctors(self, x_pts):
+        x = np.ascontiguousarray(np.asarray(x_pts, dtype=np.float64).reshape(-1, 3))
+        n = len(x)
+        d = self.prog.dim
+        coll = native.collapse_mask(self.prog, self.collapse)
+        shape = [1 if (coll >> a) & 1 else self.n for a in range(d)]
+        bs = 1 if self.prog.kind == 0 else d
+        chi = np.zeros((n, self.m, bs) + tuple(reversed(shape)))
+        A = np.zeros((n, self.m, self.m))
+        P = CellParams()
+        P.n_pts, P.x_pts, P.A_hom, P.chi = n, x.ctypes.data, A.ctypes.data, chi.ctypes.data
+        self._launch(P, n)
+        return chi
 
     def local_matrices(self, cell_nodes, node_xyz):
         cells = np.ascontiguousarray(cell_nodes, dtype=np.int32)

@@ -83,3 +83,33 @@ def test_axis_collapse_is_exact(name):
     for k in range(len(x)):
         Ao = K.oracle_tensor(case, mic, x[k])
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+
+
+@pytest.mark.parametrize("name,collapse", [("p2_fulltensor_strat_n9", False), ("p3_smooth_n4", True), ("e2_hooke_sin_strat_n7", False),
+                                           ("e3_fibre_rot_n4", True), ("e3_hooke_smooth_n4", False)])  # fmt: skip
+def test_correctors_match_oracle(name, collapse):
+    """chi_q (hmm.py:1211-1213) up to the additive constants the periodic problem leaves free."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-12, collapse=collapse)
+    x = K.points(case, 1)
+    chi = s.correctors(x)[0]  # (n_rhs, bs, [z,] y, x) possibly with collapsed axes of extent 1
+    d, n = case.dim, case.n
+    chi = np.broadcast_to(chi, chi.shape[:2] + (n,) * d)
+    mic = K.oracle_cell(case, prog)
+    import coefficients as Cf
+    from oracle import npufl
+
+    M = None
+    if case.dtheta:
+        M = np.asarray(getattr(Cf, case.dtheta)(npufl)(x[0]))[..., 0]
+    _, chis = ho.cell_tensor(mic, getattr(Cf, case.coeff)(npufl), x[0], M, return_correctors=True)
+    # oracle dofs: periodic node id (np.unique order of master vertices = natural order), comps interleaved
+    bs = mic.bs
+    scale = max(np.abs(c - c.mean()).max() for c in chis)
+    for q in range(len(chis)):
+        co = chis[q].reshape(-1, bs).T.reshape((bs,) + (n,) * d)  # natural order: slowest axis first
+        for k in range(bs):
+            a, b = chi[q, k] - chi[q, k].mean(), co[k] - co[k].mean()
+            assert np.abs(a - b).max() <= 1e-8 * scale + 1e-14, (q, k)

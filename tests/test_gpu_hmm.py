@@ -162,3 +162,9 @@ def test_hmm_equals_periodic_homogenisation():
     mic = ho.MicroCell(omesh.create_unit_square(n, n), "poisson", 3)
     Ao = ho.cell_tensor(mic, Cf.periodic_only(npufl), [0.0, 0.0, 0.0])
     assert np.abs(per.A_hom - Ao).max() <= 1e-10 * np.abs(Ao).max()
+    # correctors on the micro mesh vertices (slaves carry their master's value), up to a constant
+    _, chis = ho.cell_tensor(mic, Cf.periodic_only(npufl), [0.0, 0.0, 0.0], return_correctors=True)
+    for q in range(2):
+        got = per.correctors[q].x.array
+        want = chis[q][mic.node2per]
+        assert np.abs((got - got.mean()) - (want - want.mean())).max() < 1e-9
