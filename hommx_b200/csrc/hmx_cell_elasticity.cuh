@@ -165,12 +165,10 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
           HMX_UNROLL
           for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -sqrtw : 0.0;
         } else {
-          // H[p][j] = sum_k Ms[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j])
-          double H[D][D];
+          // e = sym(H) accumulated directly in engineering Voigt form,
+          // H[p][j] = sum_k Ms[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j]):  e[voigt(p,j)] += Ms[p][pi(k)] dk[j]
           HMX_UNROLL
-          for (int p = 0; p < D; ++p)
-            HMX_UNROLL
-            for (int j = 0; j < D; ++j) H[p][j] = 0.0;
+          for (int v = 0; v < NV; ++v) e[v] = 0.0;
           HMX_UNROLL
           for (int k2 = 0; k2 < D; ++k2) {
             const int ax = kuhn_axis<D>(t, k2);
@@ -180,19 +178,14 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
               const double dk = u[b1][j] - u[b0][j];
               HMX_UNROLL
               for (int p = 0; p < D; ++p)
-                if (!HMX_MZ(p, ax)) H[p][j] += Ms[p * D + ax] * dk;
+                if (!HMX_MZ(p, ax)) {
+                  // Voigt slot of the (p, j) entry: diagonal -> p, off-diagonal pairs in the order (0,1)[,(0,2),(1,2)]
+                  const int lo = p < j ? p : j, hi = p < j ? j : p;
+                  const int v = p == j ? p : D + (lo == 0 ? hi - 1 : 2);
+                  e[v] += Ms[p * D + ax] * dk;
+                }
             }
           }
-          HMX_UNROLL
-          for (int v = 0; v < D; ++v) e[v] = H[v][v];
-          int v = D;
-          HMX_UNROLL
-          for (int r = 0; r < D; ++r)
-            HMX_UNROLL
-            for (int c = r + 1; c < D; ++c) {
-              e[v] = H[r][c] + H[c][r];
-              ++v;
-            }
         }
         double sa[NA1], sig[NV];
         HMX_UNROLL
@@ -215,14 +208,28 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         for (int k2 = 0; k2 < D; ++k2) {
           const int ax = kuhn_axis<D>(t, k2);
           const int b0 = kuhn_pmask<D>(t, k2), b1 = kuhn_pmask<D>(t, k2 + 1);
+          // single-term columns (e.g. the rotation axis of C4's Jacobian) go straight into the two
+          // accumulators as FMAs; longer ones are summed once and added / subtracted
+          int nterms = 0;
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p) nterms += HMX_MZ(p, ax) ? 0 : 1;
           HMX_UNROLL
           for (int j = 0; j < D; ++j) {
-            double tk = 0.0;
-            HMX_UNROLL
-            for (int p = 0; p < D; ++p)
-              if (!HMX_MZ(p, ax)) tk += S[j][p] * Ms[p * D + ax];
-            acc[b1][j] += tk;
-            acc[b0][j] -= tk;
+            if (nterms == 1) {
+              HMX_UNROLL
+              for (int p = 0; p < D; ++p)
+                if (!HMX_MZ(p, ax)) {
+                  acc[b1][j] += S[j][p] * Ms[p * D + ax];
+                  acc[b0][j] -= S[j][p] * Ms[p * D + ax];
+                }
+            } else {
+              double tk = 0.0;
+              HMX_UNROLL
+              for (int p = 0; p < D; ++p)
+                if (!HMX_MZ(p, ax)) tk += S[j][p] * Ms[p * D + ax];
+              acc[b1][j] += tk;
+              acc[b0][j] -= tk;
+            }
           }
         }
       }
