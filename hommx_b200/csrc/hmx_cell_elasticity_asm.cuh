@@ -11,15 +11,21 @@
 // matrix-free kernel.  Each block is loaded once per iteration and reused by all D(D+1)/2
 // right-hand sides from registers (54 FMA per 9 loaded doubles).
 //
-// Thread i owns node i and all right-hand sides: y = K p in registers, p and r in shared memory
-// (node-major, 16-byte loads of the neighbours' p), x and the matrix in the L2-resident scratch.
-// Only the diagonal block and the blocks of the 2^D-1 POSITIVE stencil directions are stored
-// (K_{i,i-d} = K_{i-d,i}^T is read from the neighbour's row): 80 doubles per node, 328 KB per 8^3
-// cell, 48 MB for 148 CTAs -- the full rows (82 MB) did not stay in the two-partition L2 (31 % of
-// the matrix reads went to DRAM, profiles/r01_c4_v4a_raw.txt).  Layout [direction][pair][node][2]:
-// a warp reads 512 consecutive bytes with one LDG.128 per thread.  No colouring, no scatter: the
-// apply is a pure gather.  Preconditioner, stopping rule and epilogue are those of
-// the matrix-free kernel (block Jacobi; A_hom = <C> - b_p.x_q - x_p.r_q).
+// Thread i owns node i and all right-hand sides: y = K p in registers (18 doubles), p and r in
+// shared memory (node-major, 16-byte loads of the neighbours' p), x, b and the matrix in the
+// L2-resident scratch.  Only the diagonal block and the blocks of the 2^D-1 POSITIVE stencil
+// directions are stored (K_{i,i-d} = K_{i-d,i}^T): 72 doubles per node, 295 KB per 8^3 cell, 44 MB for
+// 148 CTAs -- full rows (82 MB) did not stay in the two-partition L2 (31 % of the matrix reads went
+// to DRAM, profiles/r01_c4_v4a_raw.txt).
+//
+// The apply is STAGED through shared memory, one stencil direction d (9 x N doubles, 36 KB) at a
+// time in a two-buffer ring: while the CTA computes  y_i += B_d[i] p_{i+d} + B_d[i-d]^T p_{i-d}  from
+// the current buffer -- so every block fetched from L2 is used twice --, each thread already holds
+// its 9 doubles of direction d+1 in flight (coalesced LDG issued before the math) and stores them
+// into the other buffer afterwards; one BAR.SYNC per stage.  Loading straight into registers
+// (first version) left the L2 latency exposed: 16 warps at 128 registers cannot keep enough
+// loads in flight (long_scoreboard 5.1 stall cycles per issue, profiles/r01_c4_v4b_raw.txt).
+// No colouring, no scatter: the apply is a pure gather.
 #pragma once
 #include "hmx_cell_common.cuh"
 #include "hmx_cell_elasticity.cuh"  // sym_inverse
@@ -44,15 +50,17 @@ struct ElasticityAsmLayout {
   static constexpr int NRC = AtomIdx<D, NM, CO::YDEP>::NRC;
   static constexpr int NREDV = 2 * NRHS > NA1 ? 2 * NRHS : NA1;
   static constexpr int o_red = 0;                          // 2 buffers [NW][NREDV]
-  static constexpr int o_atoms = o_red + 2 * NW * NREDV;   // [NA][T][NRC]
-  static constexpr int o_dinv = ((o_atoms + NA1 * T * NRC + 1) / 2) * 2;  // [NSYM][N]
-  static constexpr int o_p = ((o_dinv + NSYM * N + 1) / 2) * 2;           // [N][NVEC]
+  static constexpr int NBQ = ((NB + 1) / 2) * 2;                          // block entries padded to 16-byte pairs
+  static constexpr int o_ring = ((o_red + 2 * NW * NREDV + 1) / 2) * 2;   // 2 x [N][NBQ] staged matrix blocks
+  static constexpr int o_atoms = o_ring;                                  // [NA][T][NRC]: dead once the matrix exists
+  static constexpr int RING = 2 * NBQ * N > NA1 * T * NRC ? 2 * NBQ * N : NA1 * T * NRC;
+  static constexpr int o_p = o_ring + RING;                               // [N][NVEC]
   static constexpr int o_r = o_p + N * NVEC;                              // [N][NVEC]
   static constexpr int total = o_r + N * NVEC;
-  static constexpr int NBP = (NB + 1) / 2;                  // block entries padded to pairs (LDG.128)
-  static constexpr int KDOUBLES = (1 + NH) * NBP * 2 * N;   // diagonal + positive directions
+  static constexpr int KDOUBLES = (1 + NH) * NB * N;        // [direction][entry][node]: diagonal + positive directions
   static constexpr int scratch_doubles = KDOUBLES + 2 * N * NVEC;  // matrix, load vectors, correctors; per CTA
   static_assert(NT >= N && NT % 32 == 0, "one thread per node");
+  static_assert(NVEC % 2 == 0, "the per-node vectors are moved with 16-byte accesses");
 };
 
 // stencil slot of the edge from local vertex a to local vertex b of a type-t simplex
@@ -89,12 +97,12 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
 
   double* sm = dyn_smem();
   double* s_red = sm + L::o_red;
-  double* s_atoms = sm + L::o_atoms;
-  double* s_dinv = sm + L::o_dinv;
+  double* s_atoms = sm + L::o_atoms;  // aliases the ring: only alive during the assembly
+  double* s_ring = sm + L::o_ring;    // 2 x [N][NBQ]
+  constexpr int NBQ = L::NBQ;
   double* s_p = sm + L::o_p;
   double* s_r = sm + L::o_r;
-  constexpr int NBP = L::NBP;
-  double* g_K = P.scratch + (size_t)bid() * L::scratch_doubles;  // [1+NH][NBP][N][2]
+  double* g_K = P.scratch + (size_t)bid() * L::scratch_doubles;  // [1+NH][NB][N]
   double* g_b = g_K + L::KDOUBLES;                               // [NVEC][N]
   double* g_x = g_b + N * NVEC;                                  // [NVEC][N]
 
@@ -153,15 +161,18 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
     }
 
     // ---- 2. assemble the row of node i: one stencil direction at a time, blocks in registers ----
+    double di[NSYM];  // inverse diagonal block of node i (thread-private -> registers)
+    HMX_UNROLL
+    for (int k = 0; k < NSYM; ++k) di[k] = 0.0;
     double r[NVEC];  // starts as the load vectors b_q[i]
     HMX_UNROLL
     for (int k = 0; k < NVEC; ++k) r[k] = 0.0;
     if (own) {
       HMX_UNROLL
       for (int d = 0; d <= NH; ++d) {  // diagonal and positive directions; the rest are transposes
-        double blk[2 * NBP];
+        double blk[NB];
         HMX_UNROLL
-        for (int k = 0; k < 2 * NBP; ++k) blk[k] = 0.0;
+        for (int k = 0; k < NB; ++k) blk[k] = 0.0;
         HMX_UNROLL
         for (int t = 0; t < T; ++t) {
           HMX_UNROLL
@@ -222,7 +233,7 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
           }
         }
         HMX_UNROLL
-        for (int k = 0; k < NBP; ++k) st_pair(g_K + ((size_t)(d * NBP + k) * N + i) * 2, blk[2 * k], blk[2 * k + 1]);
+        for (int k = 0; k < NB; ++k) g_K[(size_t)(d * NB + k) * N + i] = blk[k];
         if (d == 0) {
           double sym[NSYM], inv[NSYM];
           HMX_UNROLL
@@ -231,14 +242,16 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
             for (int j2 = j; j2 < D; ++j2) sym[sym_index(D, j, j2)] = blk[j * D + j2];
           sym_inverse<D>(sym, inv);
           HMX_UNROLL
-          for (int k = 0; k < NSYM; ++k) s_dinv[k * N + i] = inv[k];
+          for (int k = 0; k < NSYM; ++k) di[k] = inv[k];
         }
       }
       HMX_UNROLL
       for (int k = 0; k < NVEC; ++k) g_b[k * N + i] = r[k];
     }
 
-    // ---- 3. PCG on all right-hand sides; r, y in registers, p, x in shared memory ----
+    sync();  // every thread is done with the atoms: their storage becomes the ring
+
+    // ---- 3. PCG on all right-hand sides; y in registers, p, r in shared memory, x in the scratch ----
     double rz[NRHS], rz0[NRHS];
     bool active[NRHS];
     {
@@ -246,9 +259,6 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
       HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) part[q] = 0.0;
       if (own) {
-        double di[NSYM];
-        HMX_UNROLL
-        for (int k = 0; k < NSYM; ++k) di[k] = s_dinv[k * N + i];
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q)
           HMX_UNROLL
@@ -261,8 +271,11 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
             s_r[i * NVEC + q * D + j] = r[q * D + j];
             g_x[(q * D + j) * N + i] = 0.0;
           }
+        // stage 0 (the diagonal blocks) of the first iteration
+        HMX_UNROLL
+        for (int k = 0; k < NB; ++k) s_ring[i * NBQ + k] = g_K[(size_t)k * N + i];
       }
-      block_sum<NRHS, NW>(part, s_red + (red_flip ^= 1) * NW * L::NREDV);  // publishes p and the matrix rows
+      block_sum<NRHS, NW>(part, s_red + (red_flip ^= 1) * NW * L::NREDV);  // publishes p and ring buffer 0
       HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) {
         rz[q] = rz0[q] = part[q];
@@ -276,51 +289,72 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
       its[q] = 0;
       any = any || active[q];
     }
+    // neighbours of node i: +mask and -mask for every positive direction
+    int jp[NH + 1], jm[NH + 1];
+    HMX_UNROLL
+    for (int d = 1; d <= NH; ++d) {
+      jp[d] = G::template shifted<1>(c, d);
+      jm[d] = G::template shifted<-1>(c, d);
+    }
+    jp[0] = jm[0] = i;
+    constexpr int NSTAGE = NH + 1;  // stage s holds direction s; buffer s & 1 (NSTAGE is even: 4 or 8)
+    static_assert(NSTAGE % 2 == 0, "the ring parity must repeat from one iteration to the next");
     while (any && it < P.max_it) {
       ++it;
       double y[NVEC], pAp[NRHS];
       HMX_UNROLL
       for (int k = 0; k < NVEC; ++k) y[k] = 0.0;
       HMX_UNROLL
+      for (int s = 0; s < NSTAGE; ++s) {
+        // (a) the loads of the next stage (next iteration's diagonal after the last one) go in flight
+        const int nxt = (s + 1) % NSTAGE;
+        double kn[NB];
+        if (own) {
+          HMX_UNROLL
+          for (int k = 0; k < NB; ++k) kn[k] = ld_stream(g_K + (size_t)(nxt * NB + k) * N + i);
+        }
+        // (b) math of this stage from ring buffer s & 1 (16-byte shared-memory loads)
+        if (own) {
+          const double* kb = s_ring + (s & 1) * NBQ * N;
+          {
+            double kk[NBQ], pj[NVEC];
+            HMX_UNROLL
+            for (int k = 0; k < NBQ; k += 2) ld_pair(kb + i * NBQ + k, kk[k], kk[k + 1]);
+            const double* pn = s_p + jp[s] * NVEC;
+            HMX_UNROLL
+            for (int k = 0; k < NVEC; k += 2) ld_pair(pn + k, pj[k], pj[k + 1]);
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q)
+              HMX_UNROLL
+              for (int j = 0; j < D; ++j)
+                HMX_UNROLL
+                for (int j2 = 0; j2 < D; ++j2) y[q * D + j] += kk[j * D + j2] * pj[q * D + j2];
+          }
+          if (s > 0) {  // the same direction seen from node i - d: the neighbour's block, transposed
+            double kk[NBQ], pj[NVEC];
+            HMX_UNROLL
+            for (int k = 0; k < NBQ; k += 2) ld_pair(kb + jm[s] * NBQ + k, kk[k], kk[k + 1]);
+            const double* pn = s_p + jm[s] * NVEC;
+            HMX_UNROLL
+            for (int k = 0; k < NVEC; k += 2) ld_pair(pn + k, pj[k], pj[k + 1]);
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q)
+              HMX_UNROLL
+              for (int j = 0; j < D; ++j)
+                HMX_UNROLL
+                for (int j2 = 0; j2 < D; ++j2) y[q * D + j] += kk[j2 * D + j] * pj[q * D + j2];
+          }
+          // (c) park the next stage in the other buffer (its readers finished a barrier ago)
+          double* kw = s_ring + ((s + 1) & 1) * NBQ * N + i * NBQ;
+          HMX_UNROLL
+          for (int k = 0; k + 1 < NB; k += 2) st_pair(kw + k, kn[k], kn[k + 1]);
+          if (NB % 2) kw[NB - 1] = kn[NB - 1];
+        }
+        if (s + 1 < NSTAGE) sync();  // after the last stage the reduction's barrier does the job
+      }
+      HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) pAp[q] = 0.0;
       if (own) {
-        // software pipeline over the stencil directions: the 16-byte loads of direction d+2 are
-        // issued before the FMAs of direction d (L2 latency ~ 2 directions of math per warp)
-        // d = 0 diagonal, 1..NH node i + mask (own block), NH+1..2NH node i - mask (neighbour's block, transposed)
-        constexpr int DEPTH = 3;
-        double kb[DEPTH][2 * NBP];
-        int jnb[NSTEN];
-        HMX_UNROLL
-        for (int d = 0; d < NSTEN; ++d)
-          jnb[d] = d == 0 ? i : (d > NH ? G::template shifted<-1>(c, d - NH) : G::template shifted<1>(c, d));
-#define HMX_LOADK(d_)                                                                                            \
-  {                                                                                                              \
-    const int dd_ = (d_) > NH ? (d_)-NH : (d_);                                                                  \
-    const int row_ = (d_) > NH ? jnb[d_] : i;                                                                    \
-    HMX_UNROLL                                                                                                   \
-    for (int k = 0; k < NBP; ++k)                                                                                \
-      ld_stream_pair(g_K + ((size_t)(dd_ * NBP + k) * N + row_) * 2, kb[(d_) % DEPTH][2 * k], kb[(d_) % DEPTH][2 * k + 1]); \
-  }
-        HMX_UNROLL
-        for (int d = 0; d < DEPTH - 1; ++d) HMX_LOADK(d);
-        HMX_UNROLL
-        for (int d = 0; d < NSTEN; ++d) {
-          if (d + DEPTH - 1 < NSTEN) HMX_LOADK(d + DEPTH - 1);
-          const bool tr = d > NH;
-          const double* pn = s_p + jnb[d] * NVEC;
-          HMX_UNROLL
-          for (int q = 0; q < NRHS; ++q) {
-            double pj[D];
-            HMX_UNROLL
-            for (int j2 = 0; j2 < D; ++j2) pj[j2] = pn[q * D + j2];
-            HMX_UNROLL
-            for (int j = 0; j < D; ++j)
-              HMX_UNROLL
-              for (int j2 = 0; j2 < D; ++j2)
-                y[q * D + j] += (tr ? kb[d % DEPTH][j2 * D + j] : kb[d % DEPTH][j * D + j2]) * pj[j2];
-          }
-        }
-#undef HMX_LOADK
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q)
           HMX_UNROLL
@@ -337,9 +371,6 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
       HMX_UNROLL
       for (int k = 0; k < NVEC; ++k) z[k] = 0.0;
       if (own) {
-        double di[NSYM];
-        HMX_UNROLL
-        for (int k = 0; k < NSYM; ++k) di[k] = s_dinv[k * N + i];
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q) {
           HMX_UNROLL

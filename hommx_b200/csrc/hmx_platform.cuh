@@ -35,6 +35,12 @@ HMX_DEV void ld_stream_pair(const double* p, double& a, double& b) {
   b = v.y;
 }
 HMX_DEV void st_pair(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+// 16-byte load from shared or global memory through the generic path (LDS.128 when p is in shared memory)
+HMX_DEV void ld_pair(const double* p, double& a, double& b) {
+  const double2 v = *reinterpret_cast<const double2*>(p);
+  a = v.x;
+  b = v.y;
+}
 HMX_DEV double* dyn_smem() {
   extern __shared__ __align__(16) double hmx_smem_[];
   return hmx_smem_;

@@ -1,0 +1,21 @@
+import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
+import numpy as np, torch
+import cases as K
+from hommx_b200 import native
+case = K.BY_NAME["e3_fibre_rot_n8_c4"]; prog = K.program(case); qp,qw = K.tables(case, prog)
+npts = 148*20
+rng = np.random.default_rng(0); x = rng.uniform(0,1,(npts,3)); x[:,1]*=0.4; x[:,2]*=0.1
+xd = torch.tensor(x, device='cuda'); 
+out = {}
+for variant in (0, 1):
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-8, variant=variant)
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    A = torch.empty((npts, 6, 6), device='cuda', dtype=torch.float64); it = torch.empty(npts, device='cuda', dtype=torch.int32)
+    best = 1e9
+    for rep in range(3):
+        e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+        e0.record(); s.cell_tensors_dev(npts, xd, A, it); e1.record(); torch.cuda.synchronize(); best=min(best,e0.elapsed_time(e1))
+    out[variant] = A.cpu().numpy()
+    print(f"variant {variant}: {s.info} {best:.2f} ms {npts/best*1e3:.0f} cells/s mean its {it.float().mean().item():.1f}", flush=True)
+    s.close()
+print("max rel diff between variants", np.abs(out[0]-out[1]).max()/np.abs(out[0]).max())

@@ -55,6 +55,10 @@ inline void ld_stream_pair(const double* p, double& a, double& b) {
   a = p[0];
   b = p[1];
 }
+inline void ld_pair(const double* p, double& a, double& b) {
+  a = p[0];
+  b = p[1];
+}
 inline void st_pair(double* p, double a, double b) {
   p[0] = a;
   p[1] = b;
