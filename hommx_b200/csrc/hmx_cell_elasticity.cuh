@@ -27,7 +27,10 @@
 
 namespace hmx {
 
-template <class CO, int NM, int NT, int COLL = 0>
+// VGLOB = 1: the search directions p and the product y = K p live in the L2-resident scratch instead of
+// shared memory -- the fallback for cells whose vectors exceed 227 KB (3-D elasticity, n >= 10): slower
+// (every gather / accumulation goes to L2) but any cell size runs.
+template <class CO, int NM, int NT, int COLL = 0, int VGLOB = 0>
 struct ElasticityLayout {
   static constexpr int D = CO::DIM;
   static constexpr int T = kuhn_ntypes<D>();
@@ -55,9 +58,9 @@ struct ElasticityLayout {
   static constexpr int o_atoms = o_stat + 4 * NRHS;            // [NA][T][NRC]
   static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][NP] inverse diagonal blocks
   static constexpr int o_p = o_dinv + NSYM * NP;               // [NRHS][D][NP]
-  static constexpr int o_y = o_p + NRHS * NDOF;                // [NRHS][D][N]
-  static constexpr int total = o_y + NRHS * NDOF;
-  static constexpr int scratch_doubles = 2 * NRHS * NDOF;      // x and r per CTA
+  static constexpr int o_y = o_p + (VGLOB ? 0 : NRHS * NDOF);  // [NRHS][D][N]
+  static constexpr int total = o_y + (VGLOB ? 0 : NRHS * NDOF);
+  static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
                 "block size must be NRHS * (a multiple or a divisor of 32)");
 };
@@ -90,10 +93,10 @@ HMX_DEV void sym_inverse(const double* a, double* inv) {
 // One sweep over the cubes by the TPR threads of right-hand side q:  y += K p  (RHSMODE = false)
 // or  y += b_q  (RHSMODE = true: every element carries the unit strain -E_q; hmm.py:898-903).
 // Ms = sqrt(|e|) n M, so that e and sigma both carry sqrt(|e|) and the nodal forces the full |e|.
-template <class CO, int NM, int NT, bool RHSMODE, int COLL = 0>
+template <class CO, int NM, int NT, bool RHSMODE, int COLL = 0, int VGLOB = 0>
 HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
                               const double* s_p, double* s_y, int q, int l, double sqrtw) {
-  using L = ElasticityLayout<CO, NM, NT, COLL>;
+  using L = ElasticityLayout<CO, NM, NT, COLL, VGLOB>;
   using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
   using PG = PGrid<CO::DIM, NM, COLL>;
@@ -250,10 +253,10 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
 #undef HMX_HALF
 }
 
-template <class CO, int NM, int NT, int COLL = 0>
+template <class CO, int NM, int NT, int COLL = 0, int VGLOB = 0>
 HMX_DEV void elasticity_cell_body(const CellParams& P) {
   static_assert((COLL & CO::YDEP) == 0, "only axes the coefficient does not depend on can be collapsed");
-  using L = ElasticityLayout<CO, NM, NT, COLL>;
+  using L = ElasticityLayout<CO, NM, NT, COLL, VGLOB>;
   using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
   using PG = PGrid<CO::DIM, NM, COLL>;
@@ -269,10 +272,10 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   double* s_stat = sm + L::o_stat;
   double* s_atoms = sm + L::o_atoms;
   double* s_dinv = sm + L::o_dinv;
-  double* s_p = sm + L::o_p;
-  double* s_y = sm + L::o_y;
   double* g_x = P.scratch + (size_t)bid() * L::scratch_doubles;  // [NRHS][D][NP]
   double* g_r = g_x + NRHS * NDOF;
+  double* s_p = VGLOB ? g_r + NRHS * NDOF : sm + L::o_p;  // VGLOB: "s_" vectors are in the L2 scratch too
+  double* s_y = VGLOB ? g_r + 2 * NRHS * NDOF : sm + L::o_y;
 
   const int t_id = tid();
   const int q = t_id / TPR, l = t_id - q * TPR;
@@ -414,7 +417,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       else
         group_sync(1 + q, TPR);
     };
-    elasticity_sweep<CO, NM, NT, true, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
+    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
     double rz, rz0;
     {
       double part = 0.0;
@@ -450,7 +453,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     while (L::SUBW ? warp_any(active && it < P.max_it) : (active && it < P.max_it)) {
       const bool mine = active && it < P.max_it;
       if (mine) ++it;
-      elasticity_sweep<CO, NM, NT, false, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
+      elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -523,7 +526,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
-    elasticity_sweep<CO, NM, NT, true, COLL>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
+    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
     sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {
       double z[2 * NRHS];

@@ -18,6 +18,9 @@
 #ifndef HMX_MINB
 #define HMX_MINB 1
 #endif
+#ifndef HMX_VGLOB
+#define HMX_VGLOB 0  // elasticity, matrix-free: 1 = search directions and products in the L2 scratch (large cells)
+#endif
 #ifndef HMX_COLL
 #define HMX_COLL 0  // bit mask of collapsed micro axes (exact symmetry reduction, hmx_cell_common.cuh)
 #endif
@@ -28,7 +31,7 @@ using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
 #elif HMX_VARIANT == 1
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #else
-using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
+using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #endif
 static_assert(HMX_VARIANT == 0 || HMX_COLL == 0, "the assembled variant has no collapsed form");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
@@ -43,7 +46,7 @@ extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
-  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
 }
 // 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree
@@ -58,7 +61,7 @@ static void emu_body(void* arg) {
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
-  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
+  hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
 }
 extern "C" void hmx_emu_info(int* out) {

@@ -119,16 +119,25 @@ def load_library():
 # ----------------------------------------------------------------------------
 # cell kernels
 # ----------------------------------------------------------------------------
-def default_variant(prog, n):
-    """Elasticity: stream the assembled operator from L2 when one thread per node is possible and p, x
-    fit in shared memory (n <= 8 in 3-D); otherwise the matrix-free element kernel."""
+def assembled_fits(prog, n):
+    """The assembled elasticity variant needs one thread per node and p, r plus the two-stage ring in shared memory."""
     if prog.kind == POISSON:
-        return MATRIX_FREE
+        return False
     d = prog.dim
     N = n**d
     nvec = d * d * (d + 1) // 2
-    smem = 8 * (2 * N * nvec + d * (d + 1) // 2 * N + max(1, prog.natoms) * (2 if d == 2 else 6) * N + 1024)
-    fits = N <= 1024 and smem <= SMEM_LIMIT
+    nbq = (d * d + 1) // 2 * 2
+    ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
+    atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * n**ndep
+    smem = 8 * (2 * N * nvec + max(2 * nbq * N, atoms) + 2 * 32 * 12 + 64)
+    return N <= 1024 and smem <= SMEM_LIMIT
+
+
+def default_variant(prog, n):
+    """Elasticity: the matrix-free element kernel; the assembled (L2-streamed) variant is opt-in."""
+    if prog.kind == POISSON:
+        return MATRIX_FREE
+    fits = assembled_fits(prog, n)
     # measured on B200 (C4): the assembled variant reaches 33.4k cell solves/s against 36.4k of the
     # matrix-free kernel (L2 latency is not hidden by 16 warps at 128 registers) -> opt-in only
     return ASSEMBLED if (fits and os.environ.get("HMX_ELASTICITY_VARIANT") == "assembled") else MATRIX_FREE
@@ -180,14 +189,33 @@ def default_min_blocks(dim, kind, n, threads):
     return max(1, min(8, 65536 // (threads * 128)))
 
 
+def vectors_in_l2(prog, n, coll=0):
+    """Matrix-free elasticity: 1 when p and y = K p of all right-hand sides do not fit in shared memory next
+    to the preconditioner and the atoms (3-D, n >= 10): they then live in the L2 scratch."""
+    if prog.kind == POISSON:
+        return 0
+    if os.environ.get("HMX_FORCE_VGLOB") == "1":  # tests: exercise the fallback on small cells
+        return 1
+    d = prog.dim
+    ext = [1 if (coll >> a) & 1 else n for a in range(d)]
+    slots = 2**d * int(np.prod([(e + 1) // 2 for e in ext]))
+    nrhs = d * (d + 1) // 2
+    ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
+    atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * (2**ndep) * ((n + 1) // 2) ** ndep
+    need = 8 * (2 * nrhs * d * slots + nrhs * slots + atoms + 2048)
+    return 1 if need > SMEM_LIMIT else 0
+
+
 def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE, coll=0):
     kind = "p" if prog.kind == POISSON else "e"
-    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}_{prog.key}_{_src_hash()}"
+    vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
+    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}g{vg}_{prog.key}_{_src_hash()}"
 
 
 def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE, coll=0):
+    vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
     return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}",
-            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}"]  # fmt: skip
+            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}", f"-DHMX_VGLOB={vg}"]  # fmt: skip
 
 
 def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False):

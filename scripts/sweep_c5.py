@@ -41,8 +41,7 @@ def fits(prog, n):
         nh = 2**d - 1
         need = 8 * (nh * N + max(d * N, max(1, prog.natoms) * (2 if d == 2 else 6) * N) + 2048)
     else:
-        nrhs = d * (d + 1) // 2
-        need = 8 * (2 * nrhs * d * N + nrhs * N + max(1, prog.natoms) * 6 * N + 1024)
+        return 1  # the vectors move to the L2 scratch when they do not fit (native.vectors_in_l2)
     return need if need <= native.SMEM_LIMIT else None
 
 

@@ -113,3 +113,21 @@ def test_correctors_match_oracle(name, collapse):
         for k in range(bs):
             a, b = chi[q, k] - chi[q, k].mean(), co[k] - co[k].mean()
             assert np.abs(a - b).max() <= 1e-8 * scale + 1e-14, (q, k)
+
+
+@pytest.mark.parametrize("name", ["e3_hooke_smooth_n4", "e2_hooke_sin_strat_n7", "e3_fibre_rot_n4"])
+def test_vectors_in_l2_fallback_matches_oracle(name, monkeypatch):
+    """Large elasticity cells keep p and K p in the L2 scratch instead of shared memory (HMX_VGLOB);
+    forced here on small cells."""
+    monkeypatch.setenv("HMX_FORCE_VGLOB", "1")
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=0)
+    assert "g1_" in os.path.basename(s.lib._name)
+    x = K.points(case, 2)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
