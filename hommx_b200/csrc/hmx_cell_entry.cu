@@ -19,7 +19,7 @@
 #define HMX_MINB 1
 #endif
 #ifndef HMX_VGLOB
-#define HMX_VGLOB 0  // elasticity, matrix-free: 1 = search directions and products in the L2 scratch (large cells)
+#define HMX_VGLOB 0  // large cells: 1 = elasticity p, K p / Poisson atoms live in the L2 scratch instead of shared memory
 #endif
 #ifndef HMX_COLL
 #define HMX_COLL 0  // bit mask of collapsed micro axes (exact symmetry reduction, hmx_cell_common.cuh)
@@ -27,7 +27,7 @@
 
 namespace {
 #if HMX_KIND == 0
-using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
+using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #elif HMX_VARIANT == 1
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #else
@@ -42,7 +42,7 @@ constexpr int kScratch = Layout::scratch_doubles;
 #ifndef HMX_EMULATE
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #if HMX_KIND == 0
-  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
@@ -57,7 +57,7 @@ extern "C" __device__ const int hmx_info[8] = {kSmemBytes, HMX_NT,  Layout::NRHS
 static void emu_body(void* arg) {
   const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
 #if HMX_KIND == 0
-  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
+  hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else

@@ -24,7 +24,9 @@
 
 namespace hmx {
 
-template <class CO, int NM, int NT, int COLL = 0>
+// AGLOB = 1: the per-element atoms live in the L2 scratch instead of shared memory (cells with many atoms
+// on a fully y-dependent coefficient, e.g. 4 atoms at n >= 10 in 3-D, exceed 227 KB otherwise).
+template <class CO, int NM, int NT, int COLL = 0, int AGLOB = 0>
 struct PoissonLayout {
   static constexpr int D = CO::DIM;
   static constexpr int T = kuhn_ntypes<D>();
@@ -49,14 +51,14 @@ struct PoissonLayout {
   static constexpr int o_p = o_K + NH * N;                           // [NRHS][N] search directions
   static constexpr int o_atoms = o_p;                                // [NA][T][NRC]: dead once the stencil and
                                                                      // load vectors exist, so it shares p's storage
-  static constexpr int total = o_p + (NRHS * N > NA1 * T * NRC ? NRHS * N : NA1 * T * NRC);
-  static constexpr int scratch_doubles = 0;
+  static constexpr int total = o_p + ((AGLOB || NRHS * N > NA1 * T * NRC) ? NRHS * N : NA1 * T * NRC);
+  static constexpr int scratch_doubles = AGLOB ? NA1 * T * NRC : 0;
 };
 
-template <class CO, int NM, int NT, int COLL = 0>
+template <class CO, int NM, int NT, int COLL = 0, int AGLOB = 0>
 HMX_DEV void poisson_cell_body(const CellParams& P) {
   static_assert((COLL & CO::YDEP) == 0, "only axes the coefficient does not depend on can be collapsed");
-  using L = PoissonLayout<CO, NM, NT, COLL>;
+  using L = PoissonLayout<CO, NM, NT, COLL, AGLOB>;
   using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
   constexpr int D = L::D, T = L::T, N = L::N, NRHS = L::NRHS, NH = L::NH, NW = L::NW;
@@ -72,7 +74,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
   double* s_ck = sm + L::o_ck;
   double* s_kap = sm + L::o_kap;
   double* s_beta = sm + L::o_beta;
-  double* s_atoms = sm + L::o_atoms;
+  double* s_atoms = AGLOB ? P.scratch + (size_t)bid() * L::scratch_doubles : sm + L::o_atoms;
   double* s_K = sm + L::o_K;
   double* s_p = sm + L::o_p;
 

@@ -192,11 +192,15 @@ def default_min_blocks(dim, kind, n, threads):
 def vectors_in_l2(prog, n, coll=0):
     """Matrix-free elasticity: 1 when p and y = K p of all right-hand sides do not fit in shared memory next
     to the preconditioner and the atoms (3-D, n >= 10): they then live in the L2 scratch."""
-    if prog.kind == POISSON:
-        return 0
     if os.environ.get("HMX_FORCE_VGLOB") == "1":  # tests: exercise the fallback on small cells
         return 1
     d = prog.dim
+    if prog.kind == POISSON:  # Poisson: the atoms move out when they do not fit next to the half stencil
+        N = n ** (d - bin(coll).count("1"))
+        ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
+        atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * n**ndep
+        need = 8 * ((2**d - 1) * N + max(d * N, atoms) + 4096)
+        return 1 if need > SMEM_LIMIT else 0
     ext = [1 if (coll >> a) & 1 else n for a in range(d)]
     slots = 2**d * int(np.prod([(e + 1) // 2 for e in ext]))
     nrhs = d * (d + 1) // 2

@@ -51,6 +51,7 @@ CASES = [
     Case("p3_fulltensor_n6", 3, 0, 6, "full_tensor_3d", threads=64),
     Case("p3_smooth_n12", 3, 0, 12, "smooth_sin", heavy=True),
     Case("p2_inclusion_n64", 2, 0, 64, "inclusion", heavy=True),
+    Case("p3_fulltensor_n10_l2", 3, 0, 10, "full_tensor_3d", heavy=True),  # 4 atoms x 6000 elements: atoms in L2
     Case("e2_hooke_sin_n6", 2, 1, 6, "hooke_sin_2d"),
     Case("e2_hooke_sin_strat_n7", 2, 1, 7, "hooke_sin_2d", "dtheta_test_stratified"),
     Case("e3_hooke_const_n3", 3, 1, 3, "hooke_const_3d"),

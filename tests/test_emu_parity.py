@@ -115,7 +115,7 @@ def test_correctors_match_oracle(name, collapse):
             assert np.abs(a - b).max() <= 1e-8 * scale + 1e-14, (q, k)
 
 
-@pytest.mark.parametrize("name", ["e3_hooke_smooth_n4", "e2_hooke_sin_strat_n7", "e3_fibre_rot_n4"])
+@pytest.mark.parametrize("name", ["e3_hooke_smooth_n4", "e2_hooke_sin_strat_n7", "e3_fibre_rot_n4", "p3_fulltensor_n6", "p2_inclusion_n16"])
 def test_vectors_in_l2_fallback_matches_oracle(name, monkeypatch):
     """Large elasticity cells keep p and K p in the L2 scratch instead of shared memory (HMX_VGLOB);
     forced here on small cells."""
@@ -123,7 +123,7 @@ def test_vectors_in_l2_fallback_matches_oracle(name, monkeypatch):
     case = K.BY_NAME[name]
     prog = K.program(case)
     qp, qw = K.tables(case, prog)
-    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=0)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=0, threads=case.threads)
     assert "g1_" in os.path.basename(s.lib._name)
     x = K.points(case, 2)
     Ah = s.cell_tensors(x)
