@@ -104,13 +104,20 @@ template <int D, int NM, int COLL = 0>
 struct PGrid {
   using G = Grid<D, NM, COLL>;
   HMX_HOSTDEV static constexpr int H(int a) { return (G::ext(a) + 1) / 2; }
+  // parity classes only along axes that have more than one node
+  HMX_HOSTDEV static constexpr int bit(int a) {
+    int b = 0;
+    for (int k = 0; k < a; ++k) b += G::ext(k) > 1 ? 1 : 0;
+    return b;
+  }
+  static constexpr int NCLS = 1 << bit(3);
   static constexpr int HC = H(0) * H(1) * H(2);
-  static constexpr int NP = (1 << D) * HC;
+  static constexpr int NP = NCLS * HC;
   HMX_DEV static int index(const int (&c)[3]) {
     int cls = 0, idx = 0, s = 1;
     HMX_UNROLL
     for (int a = 0; a < D; ++a) {
-      cls |= (c[a] & 1) << a;
+      if (G::ext(a) > 1) cls |= (c[a] & 1) << bit(a);
       idx += (c[a] >> 1) * s;
       s *= H(a);
     }
@@ -124,7 +131,7 @@ struct PGrid {
     for (int a = 0; a < 3; ++a) {
       c[a] = 0;
       if (a < D) {
-        c[a] = 2 * (r % H(a)) + ((cls >> a) & 1);
+        c[a] = 2 * (r % H(a)) + (G::ext(a) > 1 ? ((cls >> bit(a)) & 1) : 0);
         r /= H(a);
         ok = ok && c[a] < G::ext(a);
       }

@@ -184,9 +184,9 @@ def default_min_blocks(dim, kind, n, threads):
     """__launch_bounds__ minimum of resident CTAs per SM (caps registers per thread).  The Poisson
     kernels are latency-bound (few PCG iterations, ~25 barriers per point): two or more CTAs per SM
     hide it; 128 registers per thread still compile without spills."""
-    if kind != POISSON:
-        return 1
-    return max(1, min(8, 65536 // (threads * 128)))
+    # (elasticity: only the small / axis-collapsed kernels have fewer than 384 threads; measured on the
+    # collapsed C4 kernel: 215k -> 276k cell solves/s going from 2 to 4-5 CTAs per SM)
+    return max(1, min(8, 65536 // (threads * 112)))
 
 
 def vectors_in_l2(prog, n, coll=0):
