@@ -28,12 +28,7 @@ HMX_DEV void group_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"
 HMX_DEV void warp_sync() { __syncwarp(); }
 // streaming load that bypasses L1 (the per-point matrix is far larger than L1): LDG.E.64.STRONG.GPU / ld.global.cg
 HMX_DEV double ld_stream(const double* p) { return __ldcg(p); }
-// 16-byte variants (LDG.E.128 / STG.E.128); the address must be 16-byte aligned
-HMX_DEV void ld_stream_pair(const double* p, double& a, double& b) {
-  const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
-  a = v.x;
-  b = v.y;
-}
+// 16-byte store (STS.128 / STG.E.128); the address must be 16-byte aligned
 HMX_DEV void st_pair(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
 // 16-byte load from shared or global memory through the generic path (LDS.128 when p is in shared memory)
 HMX_DEV void ld_pair(const double* p, double& a, double& b) {
@@ -58,10 +53,5 @@ HMX_DEV double seg_sum(double v, int width) {
 }
 HMX_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
-HMX_DEV double warp_max(double v) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, m));
-  return v;
-}
 }  // namespace hmx
 #endif

@@ -51,10 +51,6 @@ inline void sync() { barrier(0, emu::g_cta->nthreads); }
 inline void group_sync(int id, int count) { barrier(id, count); }
 inline void warp_sync() { barrier(16 + emu::g_cta->cur / 32, 32); }
 inline double ld_stream(const double* p) { return *p; }
-inline void ld_stream_pair(const double* p, double& a, double& b) {
-  a = p[0];
-  b = p[1];
-}
 inline void ld_pair(const double* p, double& a, double& b) {
   a = p[0];
   b = p[1];
@@ -109,15 +105,4 @@ inline bool warp_any(bool p) {
   return any;
 }
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
-inline double warp_max(double v) {
-  emu::Cta* c = emu::g_cta;
-  const int me = c->cur, par = c->wpar[me];
-  c->wbuf[par * c->nthreads + me] = v;
-  c->wpar[me] = par ^ 1;
-  barrier(16 + me / 32, 32);
-  const int w0 = (me / 32) * 32;
-  double m = c->wbuf[par * c->nthreads + w0];
-  for (int l = 1; l < 32; ++l) m = fmax(m, c->wbuf[par * c->nthreads + w0 + l]);
-  return m;
-}
 }  // namespace hmx
