@@ -44,6 +44,25 @@ def _tetrahedron_volume(points):
     return abs(np.linalg.det(np.array([p[1] - p[0], p[2] - p[0], p[3] - p[0]]))) / 6.0
 
 
+def _macro_solve(A, b, options):
+    """Stand-in for the macro PETSc KSP (outside the hot path).  Small systems and ``pc_type: lu`` use a
+    sparse direct solve; larger ones Jacobi-preconditioned CG (the lifted HMM matrix is symmetric positive
+    definite for symmetric coefficients), honouring ``ksp_rtol`` / ``ksp_atol`` / ``ksp_max_it``, with the
+    direct solve as the last resort."""
+    n = A.shape[0]
+    if n <= 20000 or options.get("pc_type") == "lu" or options.get("ksp_type") == "preonly":
+        return spla.spsolve(A.tocsc(), b)
+    rtol = float(options.get("ksp_rtol", 1e-12))
+    atol = float(options.get("ksp_atol", 0.0))
+    d = A.diagonal()
+    if np.all(d > 0):
+        M = spla.LinearOperator(A.shape, lambda v: v / d)
+        x, info = spla.cg(A, b, M=M, rtol=rtol, atol=atol, maxiter=int(options.get("ksp_max_it", 20000)))
+        if info == 0 and np.all(np.isfinite(x)) and np.linalg.norm(A @ x - b) <= 1e-9 * max(np.linalg.norm(b), 1e-300):
+            return x
+    return spla.spsolve(A.tocsc(), b)
+
+
 class BaseHMM:
     """Common driver (mirrors ``BaseHMM``, hmm.py:53-511)."""
 
@@ -271,8 +290,8 @@ class BaseHMM:
             A = (Dk @ A @ Dk + sp.diags(1.0 - keep)).tocsr()
             b[bc.dofs] = bc.values
         self._b = b
-        # macro solve: PETSc KSP in the reference (hmm.py:482-483); a direct scipy solve here
-        x = spla.spsolve(A.tocsc(), b)
+        # macro solve: PETSc KSP in the reference (hmm.py:482-483, default GMRES + ILU); scipy here
+        x = _macro_solve(A, b, self._petsc_options_global_solve)
         if not np.all(np.isfinite(x)):  # hmm.py:485-488: logged, not raised
             self._logger.error("Something went wrong in the global problem solve.")
         self._u.x.array[:] = x
@@ -433,5 +452,5 @@ class PoissonPeriodicHMM:
             Dk = sp.diags(keep)
             A = (Dk @ A @ Dk + sp.diags(1.0 - keep)).tocsr()
             b[bc.dofs] = bc.values
-        self._u.x.array[:] = spla.spsolve(A.tocsc(), b)
+        self._u.x.array[:] = _macro_solve(A, b, self._petsc_options_global_solve or {})
         return self._u
