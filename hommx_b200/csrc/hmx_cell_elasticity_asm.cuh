@@ -86,6 +86,96 @@ HMX_DEV void basis_strain(const double (&m)[D], int j, double (&e)[D * (D + 1) /
     }
 }
 
+// Row of node i of the periodic stiffness matrix, one stencil direction at a time (blocks in registers):
+// diagonal + positive directions go to g_K as [direction][entry][node]; also returns the inverse diagonal
+// block `di` and the load vectors `r` (b_q[i] for every right-hand side).
+template <class CO, int NM>
+HMX_DEV void asm_assemble_row(const int (&c)[3], int i, const double* pc, const double (&Mn)[CO::DIM * CO::DIM],
+                              const double* s_atoms, double vol, double* g_K, double (&di)[CO::DIM * (CO::DIM + 1) / 2],
+                              double (&r)[CO::DIM * CO::DIM * (CO::DIM + 1) / 2]) {
+  using G = Grid<CO::DIM, NM>;
+  using AI = AtomIdx<CO::DIM, NM, CO::YDEP>;
+  constexpr int D = CO::DIM, T = kuhn_ntypes<D>(), N = G::N, NRHS = D * (D + 1) / 2, NV = NRHS, NH = (1 << D) - 1;
+  constexpr int NB = D * D, NA = CO::NATOMS, NA1 = NA > 0 ? NA : 1, NSYM = D * (D + 1) / 2, NRC = AI::NRC;
+  HMX_UNROLL
+  for (int d = 0; d <= NH; ++d) {  // diagonal and positive directions; the rest are transposes
+    double blk[NB];
+    HMX_UNROLL
+    for (int k = 0; k < NB; ++k) blk[k] = 0.0;
+    HMX_UNROLL
+    for (int t = 0; t < T; ++t) {
+      HMX_UNROLL
+      for (int a = 0; a <= D; ++a) {
+        // does the type-t simplex in which node i is vertex a have an edge in direction d ?
+        bool any_b = false;
+        HMX_UNROLL
+        for (int b = 0; b <= D; ++b) any_b = any_b || sten_slot<D>(t, a, b) == d;
+        if (!any_b) continue;
+        int o[3];
+        G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
+        const int ro = AI::ridx(o);
+        double sa[NA1];
+        HMX_UNROLL
+        for (int k = 0; k < NA1; ++k) sa[k] = NA > 0 ? s_atoms[(k * T + t) * NRC + ro] : 0.0;
+        double ma[D];
+        HMX_UNROLL
+        for (int p = 0; p < D; ++p) {
+          ma[p] = 0.0;
+          if (a >= 1) ma[p] += Mn[p * D + kuhn_axis<D>(t, a >= 1 ? a - 1 : 0)];
+          if (a < D) ma[p] -= Mn[p * D + kuhn_axis<D>(t, a < D ? a : 0)];
+        }
+        double sg[D][NV];
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          double ea[NV];
+          basis_strain<D>(ma, j, ea);
+          CO::stress(pc, sa, ea, sg[j]);
+          if (d == 0) {
+            // load vectors ride along with the diagonal block: b_q[i][j] -= |e| (C E_q) : e(phi_a e_j)
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) r[q * D + j] -= vol * sg[j][q];  // (C ea)[q] = ea : C : E_q
+          }
+        }
+        HMX_UNROLL
+        for (int b = 0; b <= D; ++b) {
+          if (sten_slot<D>(t, a, b) != d) continue;
+          double mb[D];
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p) {
+            mb[p] = 0.0;
+            if (b >= 1) mb[p] += Mn[p * D + kuhn_axis<D>(t, b >= 1 ? b - 1 : 0)];
+            if (b < D) mb[p] -= Mn[p * D + kuhn_axis<D>(t, b < D ? b : 0)];
+          }
+          HMX_UNROLL
+          for (int j2 = 0; j2 < D; ++j2) {
+            double eb[NV];
+            basis_strain<D>(mb, j2, eb);
+            HMX_UNROLL
+            for (int j = 0; j < D; ++j) {
+              double s = 0.0;
+              HMX_UNROLL
+              for (int v = 0; v < NV; ++v) s += sg[j][v] * eb[v];
+              blk[j * D + j2] += vol * s;
+            }
+          }
+        }
+      }
+    }
+    HMX_UNROLL
+    for (int k = 0; k < NB; ++k) g_K[(size_t)(d * NB + k) * N + i] = blk[k];
+    if (d == 0) {
+      double sym[NSYM], inv[NSYM];
+      HMX_UNROLL
+      for (int j = 0; j < D; ++j)
+        HMX_UNROLL
+        for (int j2 = j; j2 < D; ++j2) sym[sym_index(D, j, j2)] = blk[j * D + j2];
+      sym_inverse<D>(sym, inv);
+      HMX_UNROLL
+      for (int k = 0; k < NSYM; ++k) di[k] = inv[k];
+    }
+  }
+}
+
 template <class CO, int NM, int NT>
 HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
   using L = ElasticityAsmLayout<CO, NM, NT>;
@@ -160,7 +250,7 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
       for (int k = 0; k < NA1; ++k) smean[k] *= 1.0 / (double)(T * NRC);
     }
 
-    // ---- 2. assemble the row of node i: one stencil direction at a time, blocks in registers ----
+    // ---- 2. assemble the row of node i (diagonal + positive directions), inverse diagonal block, loads ----
     double di[NSYM];  // inverse diagonal block of node i (thread-private -> registers)
     HMX_UNROLL
     for (int k = 0; k < NSYM; ++k) di[k] = 0.0;
@@ -168,87 +258,10 @@ HMX_DEV void elasticity_asm_cell_body(const CellParams& P) {
     HMX_UNROLL
     for (int k = 0; k < NVEC; ++k) r[k] = 0.0;
     if (own) {
-      HMX_UNROLL
-      for (int d = 0; d <= NH; ++d) {  // diagonal and positive directions; the rest are transposes
-        double blk[NB];
-        HMX_UNROLL
-        for (int k = 0; k < NB; ++k) blk[k] = 0.0;
-        HMX_UNROLL
-        for (int t = 0; t < T; ++t) {
-          HMX_UNROLL
-          for (int a = 0; a <= D; ++a) {
-            // does the type-t simplex in which node i is vertex a have an edge in direction d ?
-            bool any_b = false;
-            HMX_UNROLL
-            for (int b = 0; b <= D; ++b) any_b = any_b || sten_slot<D>(t, a, b) == d;
-            if (!any_b) continue;
-            int o[3];
-            G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
-            const int ro = AI::ridx(o);
-            double sa[NA1];
-            HMX_UNROLL
-            for (int k = 0; k < NA1; ++k) sa[k] = NA > 0 ? s_atoms[(k * T + t) * NRC + ro] : 0.0;
-            double ma[D];
-            HMX_UNROLL
-            for (int p = 0; p < D; ++p) {
-              ma[p] = 0.0;
-              if (a >= 1) ma[p] += Mn[p * D + kuhn_axis<D>(t, a >= 1 ? a - 1 : 0)];
-              if (a < D) ma[p] -= Mn[p * D + kuhn_axis<D>(t, a < D ? a : 0)];
-            }
-            double sg[D][NV];
-            HMX_UNROLL
-            for (int j = 0; j < D; ++j) {
-              double ea[NV];
-              basis_strain<D>(ma, j, ea);
-              CO::stress(pc, sa, ea, sg[j]);
-              if (d == 0) {
-                // load vectors ride along with the diagonal block: b_q[i][j] -= |e| (C E_q) : e(phi_a e_j)
-                HMX_UNROLL
-                for (int q = 0; q < NRHS; ++q) r[q * D + j] -= vol * sg[j][q];  // (C ea)[q] = ea : C : E_q
-              }
-            }
-            HMX_UNROLL
-            for (int b = 0; b <= D; ++b) {
-              if (sten_slot<D>(t, a, b) != d) continue;
-              double mb[D];
-              HMX_UNROLL
-              for (int p = 0; p < D; ++p) {
-                mb[p] = 0.0;
-                if (b >= 1) mb[p] += Mn[p * D + kuhn_axis<D>(t, b >= 1 ? b - 1 : 0)];
-                if (b < D) mb[p] -= Mn[p * D + kuhn_axis<D>(t, b < D ? b : 0)];
-              }
-              HMX_UNROLL
-              for (int j2 = 0; j2 < D; ++j2) {
-                double eb[NV];
-                basis_strain<D>(mb, j2, eb);
-                HMX_UNROLL
-                for (int j = 0; j < D; ++j) {
-                  double s = 0.0;
-                  HMX_UNROLL
-                  for (int v = 0; v < NV; ++v) s += sg[j][v] * eb[v];
-                  blk[j * D + j2] += vol * s;
-                }
-              }
-            }
-          }
-        }
-        HMX_UNROLL
-        for (int k = 0; k < NB; ++k) g_K[(size_t)(d * NB + k) * N + i] = blk[k];
-        if (d == 0) {
-          double sym[NSYM], inv[NSYM];
-          HMX_UNROLL
-          for (int j = 0; j < D; ++j)
-            HMX_UNROLL
-            for (int j2 = j; j2 < D; ++j2) sym[sym_index(D, j, j2)] = blk[j * D + j2];
-          sym_inverse<D>(sym, inv);
-          HMX_UNROLL
-          for (int k = 0; k < NSYM; ++k) di[k] = inv[k];
-        }
-      }
+      asm_assemble_row<CO, NM>(c, i, pc, Mn, s_atoms, vol, g_K, di, r);
       HMX_UNROLL
       for (int k = 0; k < NVEC; ++k) g_b[k * N + i] = r[k];
     }
-
     sync();  // every thread is done with the atoms: their storage becomes the ring
 
     // ---- 3. PCG on all right-hand sides; y in registers, p, r in shared memory, x in the scratch ----

@@ -5,13 +5,14 @@
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
 #ifndef HMX_VARIANT
-#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator streamed from L2
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator (barrier-staged), 2 = assembled, TMA-staged
 #endif
 #if HMX_KIND == 0
 #include "hmx_cell_poisson.cuh"
 #else
 #include "hmx_cell_elasticity.cuh"
 #include "hmx_cell_elasticity_asm.cuh"
+#include "hmx_cell_elasticity_tma.cuh"
 #endif
 #include HMX_COEFF_FILE
 
@@ -30,6 +31,8 @@ namespace {
 using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #elif HMX_VARIANT == 1
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+#elif HMX_VARIANT == 2
+using Layout = hmx::ElasticityTmaLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #else
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #endif
@@ -45,6 +48,8 @@ extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 2
+  hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
@@ -60,6 +65,8 @@ static void emu_body(void* arg) {
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 2
+  hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif

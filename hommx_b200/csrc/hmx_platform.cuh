@@ -52,6 +52,46 @@ HMX_DEV double seg_sum(double v, int width) {
   return v;
 }
 HMX_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+// ---- mbarrier + bulk async copy (TMA 1-D): the producer/consumer pipeline of the TMA-staged kernel ----
+// An MBar occupies HMX_MBAR_BYTES of shared memory (8 used on the device; the CPU emulation needs more).
+#define HMX_MBAR_BYTES 32
+struct MBar {
+  unsigned long long v;
+};
+HMX_DEV unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+HMX_DEV void mbar_init(MBar* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(b)) : "memory");
+}
+// make the initialised barriers visible to the async proxy (TMA) before first use; follow with a CTA barrier
+HMX_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+HMX_DEV void mbar_arrive(MBar* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+HMX_DEV void mbar_arrive_expect_tx(MBar* b, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+// true when the phase with the given parity has completed
+HMX_DEV bool mbar_try_wait(MBar* b, unsigned parity) {
+  unsigned done;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(b)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+HMX_DEV void mbar_wait(MBar* b, unsigned parity) {
+  while (!mbar_try_wait(b, parity)) {
+  }
+}
+// cp.async.bulk global -> shared (UBLKCP in SASS); bytes multiple of 16, both addresses 16-byte aligned;
+// completion is signalled on `b` as transaction bytes
+HMX_DEV void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, MBar* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+HMX_DEV void mbar_inval(MBar* b) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory"); }
+// order this thread's generic-proxy writes (global / shared) before later async-proxy (TMA) accesses
+HMX_DEV void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 }  // namespace hmx
 #endif

@@ -27,8 +27,8 @@ KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh",
-            "hmx_cell_elasticity_asm.cuh", "hmx_cell_entry.cu")
-MATRIX_FREE, ASSEMBLED = 0, 1
+            "hmx_cell_elasticity_asm.cuh", "hmx_cell_elasticity_tma.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, ASSEMBLED, ASSEMBLED_TMA = 0, 1, 2
 SMEM_LIMIT = 227 * 1024
 
 
@@ -133,6 +133,20 @@ def assembled_fits(prog, n):
     return N <= 1024 and smem <= SMEM_LIMIT
 
 
+def tma_fits(prog, n):
+    """The TMA-staged assembled variant: one thread per node with N a multiple of 32, p plus at least two ring
+    stages in shared memory."""
+    if prog.kind == POISSON:
+        return False
+    d = prog.dim
+    N = n**d
+    nvec = d * d * (d + 1) // 2
+    ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
+    atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * n**ndep
+    fixed = 8 * (N * nvec + atoms + 2 * (N // 32) * 12 + 64)
+    return N % 32 == 0 and N <= 1024 and fixed + 2 * 8 * d * d * N <= SMEM_LIMIT
+
+
 def default_variant(prog, n):
     """Elasticity: the matrix-free element kernel; the assembled (L2-streamed) variant is opt-in."""
     if prog.kind == POISSON:
@@ -155,6 +169,8 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
     N = n ** (dim - bin(coll).count("1"))
     if kind != POISSON and variant == ASSEMBLED:
         return max(64, 32 * (-(-N // 32)))  # one thread per node
+    if kind != POISSON and variant == ASSEMBLED_TMA:
+        return N  # one thread per node (N % 32 == 0)
     if kind == POISSON:
         # four nodes per thread and several CTAs per SM beat two nodes per thread and one CTA
         # (measured on B200, scripts/probe_occ.py: C3 12.2M -> 19.0M, C2 7.0M -> 11.6M points/s)

@@ -104,5 +104,44 @@ inline bool warp_any(bool p) {
   for (int l = 0; l < 32; ++l) any = any || c->wbuf[par * c->nthreads + w0 + l] != 0.0;
   return any;
 }
+// ---- mbarrier + bulk copy emulation: phase bit, pending arrivals, outstanding transaction bytes ----
+#define HMX_MBAR_BYTES 32
+struct MBar {
+  int init_count, pending;
+  long long tx;
+  unsigned phase;
+};
+inline void mbar_maybe_complete(MBar* b) {
+  if (b->pending == 0 && b->tx == 0) {
+    b->phase ^= 1u;
+    b->pending = b->init_count;
+  }
+}
+inline void mbar_init(MBar* b, int count) {
+  b->init_count = b->pending = count;
+  b->tx = 0;
+  b->phase = 0;
+}
+inline void mbar_fence_init() {}
+inline void mbar_arrive(MBar* b) {
+  --b->pending;
+  mbar_maybe_complete(b);
+}
+inline void mbar_arrive_expect_tx(MBar* b, unsigned bytes) {
+  b->tx += bytes;
+  --b->pending;
+  mbar_maybe_complete(b);
+}
+inline bool mbar_try_wait(MBar* b, unsigned parity) { return b->phase != parity; }
+inline void mbar_wait(MBar* b, unsigned parity) {
+  while (!mbar_try_wait(b, parity)) emu::yield();
+}
+inline void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, MBar* b) {
+  __builtin_memcpy(smem_dst, gmem_src, bytes);  // lands "instantly"; ordering bugs must be caught on the device
+  b->tx -= bytes;
+  mbar_maybe_complete(b);
+}
+inline void mbar_inval(MBar*) {}
+inline void fence_async_proxy() {}
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 }  // namespace hmx

@@ -29,6 +29,22 @@ def test_cell_tensor_matches_oracle(case):
 
 
 ELAST = [c for c in LIGHT if c.kind == 1]
+ELAST_TMA = [c for c in ELAST if (c.n**c.dim) % 32 == 0]
+
+
+@pytest.mark.parametrize("case", ELAST_TMA, ids=[c.name for c in ELAST_TMA])
+def test_tma_staged_elasticity_variant_matches_oracle(case):
+    """The opt-in assembled variant whose matrix blocks arrive through a TMA / mbarrier ring (the emulation
+    models the barrier protocol -- phases, transaction bytes, multi-point reuse -- not the asynchrony)."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=2, grid=2)
+    x = K.points(case, 5)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
 
 
 @pytest.mark.parametrize("case", ELAST, ids=[c.name for c in ELAST])

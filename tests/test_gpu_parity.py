@@ -89,6 +89,25 @@ def test_axis_collapse_is_exact(case):
     s.close()
 
 
+ELAST_TMA = [c for c in ALL if c.kind == 1 and native.tma_fits(K.program(c), c.n)]
+
+
+@pytest.mark.parametrize("case", ELAST_TMA, ids=[c.name for c in ELAST_TMA])
+def test_tma_staged_elasticity_variant_matches_oracle(case):
+    """Opt-in variant: assembled operator streamed through a cp.async.bulk / mbarrier ring."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=native.ASSEMBLED_TMA)
+    s.set_grid(3)  # several macro points per CTA: barriers are re-initialised between points
+    x = K.points(case, 8)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    s.close()
+
+
 def test_many_points_grid_stride():
     """More points than resident CTAs: every point is computed exactly once (persistent grid)."""
     case = K.BY_NAME["p2_smooth_n16_c1"]
