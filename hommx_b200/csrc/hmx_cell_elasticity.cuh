@@ -145,9 +145,15 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
           o[a] = a < D ? (cls[a] == 2 ? G::ext(a) - 1 : 2 * idx + cls[a]) : 0;
         }
       }
+      // Along a collapsed axis both ends of an edge are the same node: corners are addressed through their
+      // canonical index (collapsed bits cleared), steps along collapsed axes contribute nothing and are
+      // dropped at compile time -- a third of the element work for C4's fibre coefficient.
+      constexpr int CM = COLL & (NC - 1);
       int node[NC];
       HMX_UNROLL
       for (int b = 0; b < NC; ++b) {
+        node[b] = 0;
+        if (b & CM) continue;
         int cb[3];
         G::template shift_coords<1>(o, b, cb);
         node[b] = PG::index(cb);
@@ -158,7 +164,7 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         HMX_UNROLL
         for (int j = 0; j < D; ++j) {
           acc[b][j] = 0.0;
-          u[b][j] = RHSMODE ? 0.0 : s_p[(q * D + j) * N + node[b]];
+          u[b][j] = (RHSMODE || (b & CM)) ? 0.0 : s_p[(q * D + j) * N + node[b]];
         }
       const int ro = AI::ridx(o);
       HMX_UNROLL
@@ -175,7 +181,8 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
           HMX_UNROLL
           for (int k2 = 0; k2 < D; ++k2) {
             const int ax = kuhn_axis<D>(t, k2);
-            const int b0 = kuhn_pmask<D>(t, k2), b1 = kuhn_pmask<D>(t, k2 + 1);
+            if ((CM >> ax) & 1) continue;  // collapsed axis: the difference is identically zero
+            const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
             HMX_UNROLL
             for (int j = 0; j < D; ++j) {
               const double dk = u[b1][j] - u[b0][j];
@@ -210,7 +217,8 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         HMX_UNROLL
         for (int k2 = 0; k2 < D; ++k2) {
           const int ax = kuhn_axis<D>(t, k2);
-          const int b0 = kuhn_pmask<D>(t, k2), b1 = kuhn_pmask<D>(t, k2 + 1);
+          if ((CM >> ax) & 1) continue;  // both ends are the same node: the two forces cancel
+          const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
           // single-term columns (e.g. the rotation axis of C4's Jacobian) go straight into the two
           // accumulators as FMAs; longer ones are summed once and added / subtracted
           int nterms = 0;
@@ -237,9 +245,11 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
         }
       }
       HMX_UNROLL
-      for (int b = 0; b < NC; ++b)
+      for (int b = 0; b < NC; ++b) {
+        if (b & CM) continue;
         HMX_UNROLL
         for (int j = 0; j < D; ++j) s_y[(q * D + j) * N + node[b]] += acc[b][j];
+      }
     }
     if (SLAB && (col + 1) % (NCOLT / NCOL_LAST) != 0)
       warp_sync();  // next colour has the same last-axis parity: only this warp's order matters
