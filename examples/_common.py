@@ -15,6 +15,7 @@ def report(name, solver, u, t_assemble, t_solve):
     print(
         f"{name}: {solver._msh.num_cells} macro cells, {solver.function_space.num_dofs} dofs | assembly {t_assemble * 1e3:.1f} ms "
         f"({solver._msh.num_cells / t_assemble:.3e} cell solves/s, device + host copies), macro solve {t_solve * 1e3:.1f} ms | "
+        f"cell kernel {solver.assembly_stats['cell_kernel_ms']:.2f} ms = {solver.assembly_stats['cell_solves_per_s']:.3e} cell solves/s | "
         f"PCG iterations mean {it.mean():.1f} max {it.max()} | u in [{u.x.array.min():.4g}, {u.x.array.max():.4g}], "
         f"|u|_2 = {np.linalg.norm(u.x.array):.6g}"
     )

@@ -152,6 +152,7 @@ class BaseHMM:
         self._rank, self._world = 0, 1
         self.cell_iterations = None
         self.cell_residuals = None
+        self.assembly_stats = None
 
     # ------------------------------------------------------------------ API surface
     @property
@@ -220,12 +221,27 @@ class BaseHMM:
         d = self._dev
         with torch.cuda.device(self._device):
             self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
             self._solver.assemble_macro_dev(
-                d["hi"] - d["lo"], d["cells"], self._msh.num_nodes, d["xyz"], self._pattern.nnz, d["ptr"], d["src"], d["vals"],
-                d["S"], d["it"], d["res"],
+                d["hi"] - d["lo"], d["cells"], self._msh.num_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"],
             )  # fmt: skip
+            ev[1].record()
+            self._solver.gather_csr_dev(self._pattern.nnz, d["ptr"], d["src"], d["S"], d["vals"])
+            ev[2].record()
             if self._world > 1:
                 self._halo_sum()
+            ev[3].record()
+            torch.cuda.synchronize()
+            n_local = d["hi"] - d["lo"]
+            cell_ms = ev[0].elapsed_time(ev[1])
+            # observability the reference lacks (it has a tqdm bar, hmm.py:310): device timings of the last assembly
+            self.assembly_stats = {
+                "macro_cells": n_local, "cell_kernel_ms": cell_ms, "gather_ms": ev[1].elapsed_time(ev[2]),
+                "halo_ms": ev[2].elapsed_time(ev[3]), "cell_solves_per_s": n_local / max(cell_ms, 1e-9) * 1e3,
+                "rhs_iterations": self._solver.rhs_iterations(reset=True), "rank": self._rank, "world": self._world,
+            }  # fmt: skip
+            self._logger.info("HMM assembly on cuda:%d: %s", self._device, self.assembly_stats)
             self.cell_iterations = d["it"].cpu().numpy()
             self.cell_residuals = d["res"].cpu().numpy()
             S = d["S"]

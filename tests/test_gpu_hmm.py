@@ -145,6 +145,8 @@ def test_elasticity_stratified_fibres_match_oracle():
     uo = ho.solve_dirichlet(Ao, b, dofs, np.zeros(len(dofs)))
     assert np.abs(u.x.array - uo).max() <= 1e-8 * np.abs(uo).max()
     assert s.cell_iterations.max() < 10000
+    st = s.assembly_stats  # device timings and iteration counts of the last assembly
+    assert st["macro_cells"] == m.num_cells and st["cell_kernel_ms"] > 0 and st["rhs_iterations"] >= s.cell_iterations.sum()
 
 
 def test_hmm_equals_periodic_homogenisation():
