@@ -45,6 +45,87 @@ __global__ void __launch_bounds__(256) hmx_halo_unpack(long long n, const long l
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
     vals[slots[j]] = buf[j];
 }
+// ---- macro system on the device (Dirichlet lifting hmm.py:453-480, Krylov solve :482-483) ----
+// b -= A u_bc on free rows; constrained rows/columns zeroed, unit diagonal, b = value (zeroRowsColumns).
+__global__ void __launch_bounds__(256) hmx_lift(long long n, const long long* __restrict__ ptr, const int* __restrict__ idx,
+                                                double* __restrict__ vals, const signed char* __restrict__ mask,
+                                                const double* __restrict__ ubc, double* __restrict__ b) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const bool fixed = mask[i] != 0;
+    double acc = 0.0;
+    for (long long k = ptr[i]; k < ptr[i + 1]; ++k) {
+      const int j = idx[k];
+      if (fixed) {
+        vals[k] = (j == i) ? 1.0 : 0.0;
+      } else if (mask[j]) {
+        acc += vals[k] * ubc[j];
+        vals[k] = 0.0;
+      }
+    }
+    b[i] = fixed ? ubc[i] : b[i] - acc;
+  }
+}
+// Jacobi-PCG building blocks; scalars live in a small device array sc[]: 0 rz, 1 pAp, 2 rz_new, 3 rz0
+__global__ void __launch_bounds__(256) hmx_pcg_init(long long n, const long long* __restrict__ ptr, const int* __restrict__ idx,
+                                                    const double* __restrict__ vals, const double* __restrict__ b,
+                                                    double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
+                                                    double* __restrict__ dinv, double* __restrict__ sc) {
+  double part = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double d = 0.0;
+    for (long long k = ptr[i]; k < ptr[i + 1]; ++k)
+      if (idx[k] == i) d = vals[k];
+    const double di = d != 0.0 ? 1.0 / d : 0.0;
+    dinv[i] = di;
+    x[i] = 0.0;
+    r[i] = b[i];
+    p[i] = di * b[i];
+    part += b[i] * di * b[i];
+  }
+  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sc[0], part);
+    atomicAdd(&sc[3], part);
+  }
+}
+__global__ void __launch_bounds__(256) hmx_pcg_spmv(long long n, const long long* __restrict__ ptr, const int* __restrict__ idx,
+                                                    const double* __restrict__ vals, const double* __restrict__ p,
+                                                    double* __restrict__ y, double* __restrict__ sc) {
+  double part = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (long long k = ptr[i]; k < ptr[i + 1]; ++k) acc += vals[k] * p[idx[k]];
+    y[i] = acc;
+    part += p[i] * acc;
+  }
+  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sc[1], part);
+}
+__global__ void __launch_bounds__(256) hmx_pcg_update(long long n, double* __restrict__ x, double* __restrict__ r,
+                                                      const double* __restrict__ p, const double* __restrict__ y,
+                                                      const double* __restrict__ dinv, double* __restrict__ sc) {
+  const double alpha = sc[1] > 0.0 ? sc[0] / sc[1] : 0.0;
+  double part = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * y[i];
+    r[i] = ri;
+    part += ri * dinv[i] * ri;
+  }
+  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&sc[2], part);
+}
+__global__ void __launch_bounds__(256) hmx_pcg_direction(long long n, const double* __restrict__ r, double* __restrict__ p,
+                                                         const double* __restrict__ dinv, const double* __restrict__ sc) {
+  const double beta = sc[0] > 0.0 ? sc[2] / sc[0] : 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = dinv[i] * r[i] + beta * p[i];
+}
+__global__ void hmx_pcg_rotate(double* sc) {  // rz <- rz_new, clear the accumulators of the next iteration
+  sc[0] = sc[2];
+  sc[1] = 0.0;
+  sc[2] = 0.0;
+}
 // FP64 peak: 8 independent DFMA chains per thread, 1024 threads/SM
 __global__ void __launch_bounds__(256) hmx_dfma_peak(double* out, int iters, double a, double b) {
   double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
@@ -145,6 +226,7 @@ struct hmx_handle {
   DevBuf qp, qw, scratch, work;
   // staging for the host-pointer entry points
   DevBuf d_x, d_A, d_it, d_res, d_cells, d_xyz, d_ptr, d_src, d_vals, d_S;
+  DevBuf m_work;  // macro PCG: r, p, y, dinv, scalars
   mutable std::string err;
   int ntypes() const { return dim == 2 ? 2 : 6; }
   int m() const { return kind == HMX_POISSON ? dim : dim * (dim + 1) / 2; }
@@ -343,7 +425,7 @@ void hmx_destroy(hmx_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->work, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
-                    &h->d_src, &h->d_vals, &h->d_S})
+                    &h->d_src, &h->d_vals, &h->d_S, &h->m_work})
     b->release();
   if (h->module && driver().ok) driver().ModuleUnload(h->module);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -530,6 +612,64 @@ int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_
   HMX_CUDA(h, cudaSetDevice(h->device));
   hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
   HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+int hmx_macro_lift_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int32_t* indices, double* csr_vals,
+                       const int8_t* bc_mask, const double* bc_values, double* b) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_dofs < 0 || (n_dofs > 0 && (!indptr || !indices || !csr_vals || !bc_mask || !bc_values || !b)))
+    return fail(h, HMX_ERR_ARG, "hmx_macro_lift: null buffer");
+  if (n_dofs == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  hmx_lift<<<grid_1d(n_dofs, 256, h->info[6]), 256, 0, h->stream>>>(n_dofs, (const long long*)indptr, indices, csr_vals,
+                                                                     (const signed char*)bc_mask, bc_values, b);
+  HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int32_t* indices, const double* csr_vals,
+                      const double* b, double* x, double rtol, double atol, int32_t max_it, int32_t* iters, double* resid) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_dofs < 0 || (n_dofs > 0 && (!indptr || !indices || !csr_vals || !b || !x)))
+    return fail(h, HMX_ERR_ARG, "hmx_macro_pcg: null buffer");
+  if (iters) *iters = 0;
+  if (resid) *resid = 0.0;
+  if (n_dofs == 0) return HMX_OK;
+  HMX_CUDA(h, cudaSetDevice(h->device));
+  const long long n = n_dofs;
+  HMX_CUDA(h, h->m_work.reserve((4 * (size_t)n + 8) * sizeof(double)));
+  double* r = h->m_work.as<double>();
+  double *p = r + n, *y = p + n, *dinv = y + n, *sc = dinv + n;
+  const int g = grid_1d(n, 256, h->info[6]);
+  const long long* ptr = (const long long*)indptr;
+  HMX_CUDA(h, cudaMemsetAsync(sc, 0, 8 * sizeof(double), h->stream));
+  hmx_pcg_init<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, b, x, r, p, dinv, sc);
+  double hs[4] = {0, 0, 0, 0};
+  HMX_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+  HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+  const double rz0 = hs[3];
+  const double tol2 = std::max(rtol * rtol * rz0, atol * atol);
+  double rz = rz0;
+  int it = 0;
+  if (max_it <= 0) max_it = 10000;
+  while (rz > tol2 && it < max_it) {
+    const int burst = std::min(16, max_it - it);  // the host looks at the residual every 16 iterations
+    for (int k = 0; k < burst; ++k) {
+      hmx_pcg_spmv<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, p, y, sc);
+      hmx_pcg_update<<<g, 256, 0, h->stream>>>(n, x, r, p, y, dinv, sc);
+      hmx_pcg_direction<<<g, 256, 0, h->stream>>>(n, r, p, dinv, sc);
+      hmx_pcg_rotate<<<1, 1, 0, h->stream>>>(sc);
+    }
+    it += burst;
+    HMX_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+    HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+    rz = hs[0];
+    if (!(rz == rz)) return fail(h, HMX_ERR_CUDA, "hmx_macro_pcg: residual is not a number (matrix not positive definite?)");
+  }
+  HMX_CUDA(h, cudaGetLastError());
+  if (iters) *iters = it;
+  if (resid) *resid = rz0 > 0.0 ? std::sqrt(rz / rz0) : 0.0;
   return HMX_OK;
 }
 

@@ -153,6 +153,7 @@ class BaseHMM:
         self.cell_iterations = None
         self.cell_residuals = None
         self.assembly_stats = None
+        self.macro_solve_stats = None
 
     # ------------------------------------------------------------------ API surface
     @property
@@ -294,8 +295,15 @@ class BaseHMM:
     # ------------------------------------------------------------------ solve (hmm.py:434-491)
     def solve(self):
         self._assemble_stiffness()
-        A = self._A.copy().tocsr()
         b = fem.assemble_load(self._V_macro, self._f)
+        opts = self._petsc_options_global_solve
+        direct = opts.get("pc_type") == "lu" or opts.get("ksp_type") == "preonly" or opts.get("hmx_macro_solver") == "host"
+        if not direct:
+            x = self._solve_on_device(b)
+            if x is not None:
+                self._u.x.array[:] = x
+                return self._u
+        A = self._A.copy().tocsr()
         for bc in self._bcs:  # Dirichlet lifting, one condition at a time as in hmm.py:453-480
             u_bc = np.zeros(self._num_global_dofs)
             u_bc[bc.dofs] = bc.values
@@ -307,11 +315,50 @@ class BaseHMM:
             b[bc.dofs] = bc.values
         self._b = b
         # macro solve: PETSc KSP in the reference (hmm.py:482-483, default GMRES + ILU); scipy here
-        x = _macro_solve(A, b, self._petsc_options_global_solve)
+        x = _macro_solve(A, b, opts)
         if not np.all(np.isfinite(x)):  # hmm.py:485-488: logged, not raised
             self._logger.error("Something went wrong in the global problem solve.")
         self._u.x.array[:] = x
         return self._u
+
+    def _solve_on_device(self, b):
+        """Dirichlet lifting (hmm.py:453-480) and the macro Krylov solve (hmm.py:482-483) on the
+        GPU: `hmx_macro_lift_dev` + Jacobi-PCG `hmx_macro_pcg_dev` on the CSR values the assembly left on the device.
+        Conditions are lifted one at a time like the reference does (so a dof named by two conditions behaves as it
+        does there: the second lifting sees the rows and columns the first one already zeroed).  Returns None if the PCG does not converge (the caller then falls back to the host solve,
+        which also handles non-symmetric coefficients)."""
+        import torch
+
+        opts = self._petsc_options_global_solve
+        n = self._num_global_dofs
+        d = self._dev
+        tdev = d["vals"].device
+        if "indptr" not in d:
+            d["indptr"] = torch.as_tensor(self._pattern.indptr, device=tdev)
+            d["indices"] = torch.as_tensor(self._pattern.indices, device=tdev)
+        with torch.cuda.device(self._device):
+            vals = torch.as_tensor(self._A_values, device=tdev).clone()  # complete values (all ranks after the halo sum)
+            t_b = torch.as_tensor(np.ascontiguousarray(b), device=tdev)
+            t_x = torch.zeros(n, dtype=torch.float64, device=tdev)
+            self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+            for bc in self._bcs:  # one condition at a time, each lifting with the matrix the previous ones left
+                mask = np.zeros(n, dtype=np.int8)
+                ubc = np.zeros(n)
+                mask[bc.dofs] = 1
+                ubc[bc.dofs] = bc.values
+                t_mask, t_ubc = torch.as_tensor(mask, device=tdev), torch.as_tensor(ubc, device=tdev)
+                self._solver.macro_lift_dev(n, d["indptr"], d["indices"], vals, t_mask, t_ubc, t_b)
+            it, res = self._solver.macro_pcg_dev(
+                n, d["indptr"], d["indices"], vals, t_b, t_x, rtol=float(opts.get("ksp_rtol", 1e-12)),
+                atol=float(opts.get("ksp_atol", 0.0)), max_it=int(opts.get("ksp_max_it", 20000)),
+            )  # fmt: skip
+            self.macro_solve_stats = {"iterations": it, "relative_residual": res}
+            x = t_x.cpu().numpy()
+            self._b = t_b.cpu().numpy()
+        if res > max(float(opts.get("ksp_rtol", 1e-12)), 1e-10) * 10 or not np.all(np.isfinite(x)):
+            self._logger.error(f"macro PCG stopped at relative residual {res:.2e} after {it} iterations; using the host solver")
+            return None
+        return x
 
     def plot_solution(self, u=None):
         """hmm.py:493-511 (needs pyvista, as in the reference)."""

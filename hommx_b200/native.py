@@ -95,6 +95,10 @@ SYMBOLS = {
     "hmx_rhs_iterations": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_macro_lift_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "hmx_macro_pcg_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_double)]),
     "hmx_measure_peaks": (C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hmx_sync": (C.c_int, [C.c_void_p]),
 }  # fmt: skip
@@ -420,6 +424,18 @@ class CellSolver:
         v = C.c_int64()
         self._check(self.lib.hmx_rhs_iterations(self._h, C.byref(v), 1 if reset else 0))
         return v.value
+
+    def macro_lift_dev(self, n_dofs, indptr, indices, csr_vals, bc_mask, bc_values, b):
+        dp = self._dp
+        self._check(self.lib.hmx_macro_lift_dev(self._h, int(n_dofs), dp(indptr), dp(indices), dp(csr_vals), dp(bc_mask),
+                                                dp(bc_values), dp(b)))  # fmt: skip
+
+    def macro_pcg_dev(self, n_dofs, indptr, indices, csr_vals, b, x, rtol=1e-12, atol=0.0, max_it=20000):
+        dp = self._dp
+        it, res = C.c_int32(), C.c_double()
+        self._check(self.lib.hmx_macro_pcg_dev(self._h, int(n_dofs), dp(indptr), dp(indices), dp(csr_vals), dp(b), dp(x),
+                                               rtol, atol, max_it, C.byref(it), C.byref(res)))  # fmt: skip
+        return it.value, res.value
 
     def halo_pack_dev(self, csr_vals, slots, n, buf):
         dp = self._dp

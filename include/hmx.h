@@ -120,6 +120,19 @@ int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset);
 int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, int64_t n, double* buf);
 int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_t n, const double* buf);
 
+/* SURVEY 8f rows 2-3 (outside the north-star hot path; the reference does this with PETSc, hmm.py:453-491):
+ * Dirichlet lifting on the device -- b -= A u_bc on the free rows, constrained rows and columns zeroed with a unit
+ * diagonal (MatZeroRowsColumns), b = value on the constrained dofs; bc_mask [n_dofs] is 1 on constrained dofs,
+ * bc_values [n_dofs] holds their values (anything elsewhere).  The CSR index arrays are those of the pattern
+ * the gather map was built for.  All pointers are device pointers. */
+int hmx_macro_lift_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int32_t* indices, double* csr_vals,
+                       const int8_t* bc_mask, const double* bc_values, double* b);
+/* Jacobi-preconditioned CG for the lifted (symmetric positive definite) macro system, x0 = 0; stops at
+ * sqrt(r.z) <= max(rtol sqrt(r0.z0), atol) or max_it.  iters / resid are HOST pointers (may be NULL).
+ * Synchronises the stream. */
+int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int32_t* indices, const double* csr_vals,
+                      const double* b, double* x, double rtol, double atol, int32_t max_it, int32_t* iters, double* resid);
+
 /* Roofline denominators measured on this device: FP64 FMA throughput (register-resident DFMA
  * chains on every SM) in TFLOP/s and a device-to-device copy in GB/s (read+write bytes). */
 int hmx_measure_peaks(int32_t device, double* fp64_tflops, double* copy_gbs);

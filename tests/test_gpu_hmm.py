@@ -170,3 +170,29 @@ def test_hmm_equals_periodic_homogenisation():
         got = per.correctors[q].x.array
         want = chis[q][mic.node2per]
         assert np.abs((got - got.mean()) - (want - want.mean())).max() < 1e-9
+
+
+def test_device_macro_solve_matches_host_solve():
+    """lifting + Jacobi-PCG on the GPU against the scipy direct solve, same assembled matrix."""
+    m = mesh.create_unit_cube(6, 5, 4)
+    mk = lambda opts: PoissonHMM(m, Cf.smooth_sin(pufl), lambda x: 1.0 + x[0], mesh.create_unit_cube(4, 4, 4), 0.125,
+                                 petsc_options_global_solve=opts, petsc_options_cell_problem=TIGHT)  # noqa: E731
+    a, b = mk(None), mk({"pc_type": "lu"})
+    V = a.function_space
+    top = fem.locate_dofs_geometrical(V, lambda x: np.isclose(x[2], 1.0))
+    for s in (a, b):
+        s.set_boundary_conditions([s._bcs[0], fem.dirichletbc(0.25, top, V)])  # overlapping conditions: lifted one by one as in hmm.py:453-480
+    ua, ub = a.solve(), b.solve()
+    assert a.macro_solve_stats["iterations"] > 0 and b.macro_solve_stats is None
+    assert np.abs(ua.x.array - ub.x.array).max() <= 1e-9 * np.abs(ub.x.array).max()
+    # elasticity with a clamped face
+    me = mesh.create_box((0, 0, 0), (1.0, 0.4, 0.1), (4, 2, 2))
+    f = lambda x: pufl.as_vector([0.0, 0.0, -1.0])  # noqa: E731
+    mk = lambda opts: LinearElasticityHMM(me, Cf.hooke_smooth_3d(pufl), f, mesh.create_unit_cube(4, 4, 4), 0.05,
+                                          petsc_options_global_solve=opts, petsc_options_cell_problem=TIGHT)  # noqa: E731
+    a, b = mk(None), mk({"ksp_type": "preonly", "pc_type": "lu"})
+    clamp = fem.locate_dofs_geometrical(a.function_space, lambda x: np.isclose(x[0], 0.0))
+    for s in (a, b):
+        s.set_boundary_conditions(fem.dirichletbc(np.zeros(3), clamp, s.function_space))
+    ua, ub = a.solve(), b.solve()
+    assert np.abs(ua.x.array - ub.x.array).max() <= 1e-8 * np.abs(ub.x.array).max()
