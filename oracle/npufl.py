@@ -118,9 +118,19 @@ def Identity(d):
     return np.eye(d).view(_Tensor)
 
 
+def _stack_nested(expr):
+    """nested lists of scalars / point arrays -> array with the point axis last (leaves broadcast)"""
+    if isinstance(expr, (list, tuple)):
+        parts = [_stack_nested(e) for e in expr]
+        n = max(p.shape[-1] for p in parts)
+        parts = [np.broadcast_to(p, p.shape[:-1] + (n,)) for p in parts]
+        return np.stack(parts, axis=0)
+    return _pt(expr)
+
+
 def as_tensor(expr, indices=None):
     if indices is None:
-        return np.asarray(expr)
+        return _stack_nested(expr) if isinstance(expr, (list, tuple)) else np.asarray(expr)
     src = list(expr.labels)
     perm = [src.index(l) for l in indices]
     return np.transpose(expr.data, perm + [expr.data.ndim - 1])

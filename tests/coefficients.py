@@ -202,3 +202,25 @@ def hooke_smooth_3d(ufl):
         lambda x, y: 2 + x[0] + ufl.sin(2 * ufl.pi * y[0]) * ufl.cos(2 * ufl.pi * y[1]),
         lambda x, y: 1.25 + 0.5 * ufl.cos(2 * ufl.pi * y[2]),
     )
+
+
+def cubic_3d(ufl):
+    """Anisotropic (cubic symmetry) elasticity tensor with three independent, y- and x-dependent moduli, written
+    component by component: exercises the general 21-component path of the coefficient front end (the reference's
+    tests only use isotropic Hooke tensors)."""
+
+    def A(x, y):
+        c11 = 3.0 + ufl.sin(2 * ufl.pi * y[0]) * ufl.cos(2 * ufl.pi * y[1])
+        c12 = 1.0 + 0.3 * x[0]
+        c44 = 0.8 + 0.2 * ufl.cos(2 * ufl.pi * y[2])
+        d = lambda a, b: 1.0 if a == b else 0.0  # noqa: E731
+
+        def comp(i, j, k, l):
+            iso = c12 * (d(i, j) * d(k, l)) + c44 * (d(i, k) * d(j, l) + d(i, l) * d(j, k))
+            if i == j == k == l:
+                return iso + (c11 - c12 - 2 * c44)
+            return iso
+
+        return ufl.as_tensor([[[[comp(i, j, k, l) for l in range(3)] for k in range(3)] for j in range(3)] for i in range(3)])
+
+    return A
