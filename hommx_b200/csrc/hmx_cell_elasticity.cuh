@@ -474,7 +474,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       const double pAp = group_sum(part);
-      const double alpha = (mine && pAp > 0.0) ? rz / pAp : 0.0;
+      const double alpha = (mine && pAp > 0.0) ? fast_div(rz, pAp) : 0.0;
       part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -503,7 +503,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         }
       }
       const double rz_new = group_sum(part);
-      const double beta = mine ? rz_new / rz : 0.0;
+      const double beta = mine ? fast_div(rz_new, rz) : 0.0;
       if (mine) {
         rz = rz_new;
         if (!(rz_new > tol2)) active = false;

@@ -349,7 +349,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       double alpha[NRHS], part[NRHS];
       HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) {
-        alpha[q] = (active[q] && pAp[q] > 0.0) ? rz[q] / pAp[q] : 0.0;
+        alpha[q] = (active[q] && pAp[q] > 0.0) ? fast_div(rz[q], pAp[q]) : 0.0;
         part[q] = 0.0;
       }
       HMX_UNROLL
@@ -367,7 +367,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       for (int q = 0; q < NRHS; ++q) {
         beta[q] = 0.0;
         if (active[q]) {
-          beta[q] = part[q] / rz[q];
+          beta[q] = fast_div(part[q], rz[q]);
           rz[q] = part[q];
           const double tol = fmax(P.rtol * P.rtol * rz0[q], P.atol * P.atol);
           if (!(part[q] > tol)) active[q] = false;

@@ -92,6 +92,18 @@ HMX_DEV void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, MBar
 HMX_DEV void mbar_inval(MBar* b) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory"); }
 // order this thread's generic-proxy writes (global / shared) before later async-proxy (TMA) accesses
 HMX_DEV void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// a / b for the PCG scalars: MUFU.RCP64H seed + two Newton steps (~6 instructions, <= 2 ulp) instead of the
+// ~35-instruction IEEE division sequence with its slow-path branch -- the divisions were a fifth of the
+// instructions of the Poisson PCG loop (profiles/r01_p2_inclusion16_raw.txt).  b must be finite and non-zero.
+HMX_DEV double fast_div(double a, double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-b, r, 1.0);
+  r = fma(r, e, r);
+  return a * r;
+}
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 }  // namespace hmx
 #endif
