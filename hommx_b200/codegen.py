@@ -315,6 +315,66 @@ def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
     pcs = {}
     atoms_h = _hoist_point_constants(atoms, pcs)
     tens_h = _hoist_point_constants(tens, pcs)
+    m = len(voigt_pairs(dim))
+    sig_exprs = []
+    if kind == ELASTICITY:
+        idx = {}
+        n = 0
+        for p in range(m):
+            for q in range(p, m):
+                idx[(p, q)] = idx[(q, p)] = n
+                n += 1
+        esym = [Expr("sym", (), ("e", q)) for q in range(m)]
+        # If the normal-normal couplings share one value c (isotropic and cubic materials: lambda / C12),
+        #   sigma_p = c tr(e) + (T_pp - c) e_p + (normal-shear couplings)      for the normal components,
+        # which saves 5 of 14 FP64 operations per simplex for Hooke.  The differences T_pp - c are formed on the
+        # affine representation (x-only coefficients fold or become point constants), not per element.
+        offdiag = [(p, q) for p in range(dim) for q in range(p + 1, dim)]
+        shared = all(affine[idx[pq]][0].key == affine[idx[offdiag[0]]][0].key
+                     and {k: c.key for k, c in affine[idx[pq]][1]} == {k: c.key for k, c in affine[idx[offdiag[0]]][1]}
+                     for pq in offdiag)  # fmt: skip
+        sig_exprs = []
+        if shared:
+            c0c, tc = affine[idx[offdiag[0]]]
+            cdict = dict(tc)
+            tr = esym[0]
+            for q in range(1, dim):
+                tr = tr + esym[q]
+            common = tens_h[idx[offdiag[0]]] * tr
+            for p in range(m):
+                if p < dim:
+                    c0p, tp = affine[idx[(p, p)]]
+                    diff = c0p - c0c
+                    keys = sorted(set(k for k, _ in tp) | set(cdict))
+                    tpd = dict(tp)
+                    for k in keys:
+                        ck = tpd.get(k, Expr.const(0.0)) - cdict.get(k, Expr.const(0.0))
+                        diff = diff + ck * Expr("sym", (), ("s", k))
+                    diff = _hoist_point_constants([diff], pcs)[0]
+                    acc = common + diff * esym[p]
+                    for q in range(dim, m):
+                        acc = acc + tens_h[idx[(p, q)]] * esym[q]
+                else:
+                    acc = Expr.const(0.0)
+                    for q in range(m):
+                        acc = acc + tens_h[idx[(p, q)]] * esym[q]
+                sig_exprs.append(acc)
+        else:
+            for p in range(m):
+                acc = Expr.const(0.0)
+                for q in range(m):
+                    acc = acc + tens_h[idx[(p, q)]] * esym[q]
+                sig_exprs.append(acc)
+    # affine coefficients: C[0*NCOMP + c] = c0_c(x), C[(1+k)*NCOMP + c] = c_ck(x)
+    aff = [c0 for c0, _ in affine]
+    for k in range(natoms):
+        for c0, terms in affine:
+            coef = Expr.const(0.0)
+            for kk, cf in terms:
+                if kk == k:
+                    coef = coef + cf
+            aff.append(coef)
+    aff_h = _hoist_point_constants(aff, pcs)
     npc = len(pcs)
 
     sym_x = {("x", k): f"x[{k}]" for k in range(3)}
@@ -334,22 +394,6 @@ def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
     te_refs = [em.ref(e) for e in tens_h]
     te_body = _body(em.lines, te_refs, "A")
 
-    # affine coefficients: C[0*NCOMP + c] = c0_c(x), C[(1+k)*NCOMP + c] = c_ck(x)
-    aff = [c0 for c0, _ in affine]
-    for k in range(natoms):
-        for c0, terms in affine:
-            coef = Expr.const(0.0)
-            for kk, cf in terms:
-                if kk == k:
-                    coef = coef + cf
-            aff.append(coef)
-    aff_h = _hoist_point_constants(aff, pcs)
-    if len(pcs) != npc:  # a coefficient appeared only here: regenerate the pc program
-        npc = len(pcs)
-        sym_pc = {("pc", k): f"pc[{k}]" for k in range(max(npc, 1))}
-        em = _Emitter(sym_x, "p")
-        pc_refs = [em.ref(e) for _, e in sorted(pcs.values(), key=lambda t: t[0])]
-        pc_body = _body(em.lines, pc_refs, "pc")
     em = _Emitter(sym_pc, "c")
     af_body = _body(em.lines, [em.ref(e) for e in aff_h], "C")
 
@@ -363,18 +407,7 @@ def build_program(A, dim, kind, Dtheta_transpose=None) -> CoefficientProgram:
     if kind == ELASTICITY:
         sym_e = {("e", k): f"e[{k}]" for k in range(m)}
         em = _Emitter({**sym_pc, **sym_s, **sym_e}, "g")
-        idx = {}
-        n = 0
-        for p in range(m):
-            for q in range(p, m):
-                idx[(p, q)] = idx[(q, p)] = n
-                n += 1
-        sig = []
-        for p in range(m):
-            acc = Expr.const(0.0)
-            for q in range(m):
-                acc = acc + tens_h[idx[(p, q)]] * Expr("sym", (), ("e", q))
-            sig.append(em.ref(acc))
+        sig = [em.ref(e) for e in sig_exprs]
         st_body = _body(em.lines, sig, "sig")
     else:
         st_body = "    (void)pc; (void)s; (void)e; (void)sig;"
