@@ -294,10 +294,8 @@ class CellSolver:
         self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
         self._h = C.c_void_p()
         self.lib = load_library()
-        cubin = compile_kernel(prog, self.n, threads, min_blocks=min_blocks, variant=variant, collapse=collapse)
+        image = kernel_image(prog, self.n, threads, min_blocks, variant, collapse)
         self.collapse_mask = collapse_mask(prog, collapse)
-        with open(cubin, "rb") as f:
-            image = f.read()
         self._image = C.create_string_buffer(image, len(image))
         qp = np.ascontiguousarray(qp, dtype=np.float64)
         qw = np.ascontiguousarray(qw, dtype=np.float64)
@@ -454,3 +452,84 @@ def measure_peaks(device=0):
     if rc != 0:
         raise HmxError(lib.hmx_last_error(None).decode())
     return f.value, c.value
+
+
+# ----------------------------------------------------------------------------
+# NVRTC: the same kernel translation unit compiled in-process (hosts without nvcc)
+# ----------------------------------------------------------------------------
+def _nvrtc():
+    for name in ("libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    try:  # the CUDA runtime wheels torch depends on ship one as well
+        import nvidia.cuda_nvrtc as pkg
+
+        lib_dir = os.path.join(os.path.dirname(pkg.__file__), "lib")
+        for f in sorted(os.listdir(lib_dir)):
+            if f.startswith("libnvrtc.so"):
+                return C.CDLL(os.path.join(lib_dir, f))
+    except Exception:
+        pass
+    raise HmxError("neither nvcc nor libnvrtc found: the cell kernels cannot be built (there is no CPU fallback)")
+
+
+def compile_kernel_nvrtc(prog: CoefficientProgram, n, threads=None, min_blocks=None, variant=None, collapse=False):
+    """cubin image (bytes) of the cell kernel, compiled with NVRTC for sm_100a; same source and macros as
+    ``compile_kernel``."""
+    threads, min_blocks, variant, coll = resolve(prog, n, threads, min_blocks, variant, collapse)
+    rt = _nvrtc()
+    with open(os.path.join(CSRC, "hmx_cell_entry.cu")) as f:
+        src = f.read()
+    headers, names = [], []
+    for h in _HEADERS[:-1]:
+        with open(os.path.join(CSRC, h)) as f:
+            headers.append(f.read().encode())
+        names.append(h.encode())
+    headers.append(prog.source.encode())
+    names.append(b"hmx_coeff_program.cuh")
+    defs = kernel_defines(prog, n, threads, "hmx_coeff_program.cuh", min_blocks, variant, coll)
+    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo"] + [d.encode() for d in defs]
+    prg = C.c_void_p()
+    rc = rt.nvrtcCreateProgram(C.byref(prg), src.encode(), b"hmx_cell_entry.cu", len(headers),
+                               (C.c_char_p * len(headers))(*headers), (C.c_char_p * len(names))(*names))  # fmt: skip
+    if rc != 0:
+        raise HmxError(f"nvrtcCreateProgram failed ({rc})")
+    try:
+        rc = rt.nvrtcCompileProgram(prg, len(opts), (C.c_char_p * len(opts))(*opts))
+        if rc != 0:
+            size = C.c_size_t()
+            rt.nvrtcGetProgramLogSize(prg, C.byref(size))
+            log = C.create_string_buffer(size.value)
+            rt.nvrtcGetProgramLog(prg, log)
+            raise HmxError(f"NVRTC failed for the cell kernel:\n{log.value.decode()[-4000:]}")
+        size = C.c_size_t()
+        if rt.nvrtcGetCUBINSize(prg, C.byref(size)) != 0 or size.value == 0:
+            raise HmxError("NVRTC produced no cubin")
+        image = C.create_string_buffer(size.value)
+        rt.nvrtcGetCUBIN(prg, image)
+        return image.raw
+    finally:
+        rt.nvrtcDestroyProgram(C.byref(prg))
+
+
+def kernel_image(prog: CoefficientProgram, n, threads=None, min_blocks=None, variant=None, collapse=False):
+    """cubin image of the cell kernel: from the in-tree cache, else built with nvcc, else (no nvcc on the host, or
+    HMX_COMPILER=nvrtc) with NVRTC; the result is cached either way."""
+    t, mb, v, coll = resolve(prog, n, threads, min_blocks, variant, collapse)
+    cubin = os.path.join(KCACHE, kernel_key(prog, n, t, mb, v, coll) + ".cubin")
+    want = os.environ.get("HMX_COMPILER", "")
+    if not os.path.exists(cubin) or want == "nvrtc":
+        have_nvcc = shutil.which("nvcc") is not None or os.path.exists("/usr/local/cuda/bin/nvcc")
+        if want == "nvrtc" or not have_nvcc:
+            image = compile_kernel_nvrtc(prog, n, threads, min_blocks, variant, collapse)
+            os.makedirs(KCACHE, exist_ok=True)
+            if want != "nvrtc":  # an explicit nvrtc request is for testing: do not overwrite the nvcc-built cache
+                with open(cubin + f".tmp{os.getpid()}", "wb") as f:
+                    f.write(image)
+                os.replace(cubin + f".tmp{os.getpid()}", cubin)
+            return image
+        compile_kernel(prog, n, threads, min_blocks=min_blocks, variant=variant, collapse=collapse)
+    with open(cubin, "rb") as f:
+        return f.read()

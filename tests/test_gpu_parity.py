@@ -189,3 +189,18 @@ def test_results_are_bitwise_reproducible(name, kw):
         for _ in range(2):
             assert np.array_equal(s.cell_tensors(x), ref)
     s.close()
+
+
+def test_nvrtc_built_kernel_matches_oracle(monkeypatch):
+    """Hosts without nvcc build the cell kernel in-process with NVRTC (same translation unit)."""
+    monkeypatch.setenv("HMX_COMPILER", "nvrtc")
+    case = K.BY_NAME["e3_fibre_rot_n4"]
+    prog = K.program(case)
+    s = _solver(case, prog)
+    x = K.points(case, 3)
+    Ah = s.cell_tensors(x)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    s.close()

@@ -127,3 +127,10 @@ def test_micro_structure_detection():
     bad[0] = [0, 1, 5]  # left-diagonal triangle
     with pytest.raises(ValueError):
         micro.detect_structure(mesh.SimplexMesh(m.x, bad, 2))
+
+
+def test_nvrtc_compiles_the_cell_kernel_without_nvcc():
+    """The in-process NVRTC path produces an sm_100a cubin from the same translation unit (no GPU needed)."""
+    prog = __import__("cases").program(__import__("cases").BY_NAME["p2_smooth_n8"])
+    image = native.compile_kernel_nvrtc(prog, 8)
+    assert image[:4] == b"\x7fELF" and len(image) > 10000
