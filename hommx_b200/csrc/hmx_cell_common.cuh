@@ -35,6 +35,11 @@ struct CellParams {
   double rtol, atol;
 };
 
+// 16-byte word for packed index tables (one LDS.128)
+struct __attribute__((aligned(16))) U4 {
+  unsigned x, y, z, w;
+};
+
 // ---- Kuhn tables ------------------------------------------------------------------
 template <int D>
 HMX_HOSTDEV constexpr int kuhn_ntypes() { return D == 2 ? 2 : 6; }

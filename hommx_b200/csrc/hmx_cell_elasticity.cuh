@@ -59,7 +59,12 @@ struct ElasticityLayout {
   static constexpr int o_dinv = o_atoms + NA1 * T * NRC;       // [NSYM][NP] inverse diagonal blocks
   static constexpr int o_p = o_dinv + NSYM * NP;               // [NRHS][D][NP]
   static constexpr int o_y = o_p + (VGLOB ? 0 : NRHS * NDOF);  // [NRHS][D][N]
-  static constexpr int total = o_y + (VGLOB ? 0 : NRHS * NDOF);
+  // per-cube index table (even NM, no collapsed axis): the corner node slots and the atom slot of every cube in
+  // sweep order, 16-bit each, so the sweep does one or two 16-byte loads instead of ~80 integer instructions
+  static constexpr bool TAB = COLL == 0 && NM % 2 == 0 && NP <= 65535 && NRC <= 65535;
+  static constexpr int TABW = D == 3 ? 2 : 1;  // 16-byte words per cube (8 + 1 or 4 + 1 indices)
+  static constexpr int o_tab = ((o_y + (VGLOB ? 0 : NRHS * NDOF) + 1) / 2) * 2;
+  static constexpr int total = o_tab + (TAB ? N * TABW * 2 : 0);
   static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
                 "block size must be NRHS * (a multiple or a divisor of 32)");
@@ -95,7 +100,7 @@ HMX_DEV void sym_inverse(const double* a, double* inv) {
 // Ms = sqrt(|e|) n M, so that e and sigma both carry sqrt(|e|) and the nodal forces the full |e|.
 template <class CO, int NM, int NT, bool RHSMODE, int COLL = 0, int VGLOB = 0>
 HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
-                              const double* s_p, double* s_y, int q, int l, double sqrtw) {
+                              const double* s_p, double* s_y, int q, int l, double sqrtw, const U4* s_tab) {
   using L = ElasticityLayout<CO, NM, NT, COLL, VGLOB>;
   using G = Grid<CO::DIM, NM, COLL>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
@@ -150,13 +155,25 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
       // dropped at compile time -- a third of the element work for C4's fibre coefficient.
       constexpr int CM = COLL & (NC - 1);
       int node[NC];
-      HMX_UNROLL
-      for (int b = 0; b < NC; ++b) {
-        node[b] = 0;
-        if (b & CM) continue;
-        int cb[3];
-        G::template shift_coords<1>(o, b, cb);
-        node[b] = PG::index(cb);
+      int ro;
+      if (L::TAB) {
+        const U4* ent = s_tab + (size_t)(col * total + k) * L::TABW;
+        const U4 w0 = ent[0];
+        const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, D == 3 ? ent[L::TABW - 1].x : 0u, D == 3 ? ent[L::TABW - 1].y : 0u,
+                               D == 3 ? ent[L::TABW - 1].z : 0u, D == 3 ? ent[L::TABW - 1].w : 0u};
+        HMX_UNROLL
+        for (int b = 0; b < NC; ++b) node[b] = (int)((w[b >> 1] >> (16 * (b & 1))) & 0xffffu);
+        ro = (int)(w[NC >> 1] & 0xffffu);
+      } else {
+        HMX_UNROLL
+        for (int b = 0; b < NC; ++b) {
+          node[b] = 0;
+          if (b & CM) continue;
+          int cb[3];
+          G::template shift_coords<1>(o, b, cb);
+          node[b] = PG::index(cb);
+        }
+        ro = AI::ridx(o);
       }
       double u[NC][D], acc[NC][D];
       HMX_UNROLL
@@ -166,7 +183,6 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
           acc[b][j] = 0.0;
           u[b][j] = (RHSMODE || (b & CM)) ? 0.0 : s_p[(q * D + j) * N + node[b]];
         }
-      const int ro = AI::ridx(o);
       HMX_UNROLL
       for (int t = 0; t < T; ++t) {
         double e[NV];
@@ -284,6 +300,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   double* s_dinv = sm + L::o_dinv;
   double* g_x = P.scratch + (size_t)bid() * L::scratch_doubles;  // [NRHS][D][NP]
   double* g_r = g_x + NRHS * NDOF;
+  U4* s_tab = reinterpret_cast<U4*>(sm + L::o_tab);
   double* s_p = VGLOB ? g_r + NRHS * NDOF : sm + L::o_p;  // VGLOB: "s_" vectors are in the L2 scratch too
   double* s_y = VGLOB ? g_r + 2 * NRHS * NDOF : sm + L::o_y;
 
@@ -295,6 +312,33 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   const double vol = (D == 2 ? 0.5 * h * h : h * h * h / 6.0) * (double)G::NLAYERS;
   const double sqrtw = sqrt(vol);
   int red_flip = 0;
+
+  if (L::TAB) {
+    // the cube -> (corner node slots, atom slot) table depends on the micro grid only: built once per launch.
+    // Entry order = sweep order: colour (last-axis parity slowest), then the cube index inside the colour.
+    constexpr int HALF = NM / 2, TOT = ipow(HALF, D), NC = 1 << D;
+    for (int idx = t_id; idx < N; idx += NT) {
+      const int col = idx / TOT;
+      int k = idx - col * TOT, cc = col, o[3] = {0, 0, 0};
+      HMX_UNROLL
+      for (int a = 0; a < D; ++a) {
+        o[a] = 2 * (k % HALF) + (cc % 2);
+        k /= HALF;
+        cc /= 2;
+      }
+      unsigned w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b) {
+        int cb[3];
+        G::template shift_coords<1>(o, b, cb);
+        w[b >> 1] |= (unsigned)PG::index(cb) << (16 * (b & 1));
+      }
+      w[NC >> 1] |= (unsigned)AI::ridx(o);
+      s_tab[(size_t)idx * L::TABW] = U4{w[0], w[1], w[2], w[3]};
+      if (D == 3) s_tab[(size_t)idx * L::TABW + 1] = U4{w[4], w[5], w[6], w[7]};
+    }
+    sync();
+  }
 
   for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {
     double xm[3], verts[(D + 1) * 3];
@@ -427,7 +471,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       else
         group_sync(1 + q, TPR);
     };
-    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = b_q
+    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);  // y = b_q
     double rz, rz0;
     {
       double part = 0.0;
@@ -463,7 +507,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     while (L::SUBW ? warp_any(active && it < P.max_it) : (active && it < P.max_it)) {
       const bool mine = active && it < P.max_it;
       if (mine) ++it;
-      elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);  // y = K p
+      elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);  // y = K p
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -536,7 +580,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
-    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw);
+    elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
     sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {
       double z[2 * NRHS];
