@@ -62,9 +62,17 @@ struct ElasticityLayout {
   // per-cube index table (even NM, no collapsed axis): the corner node slots and the atom slot of every cube in
   // sweep order, 16-bit each, so the sweep does one or two 16-byte loads instead of ~80 integer instructions
   static constexpr bool TAB = COLL == 0 && NM % 2 == 0 && NP <= 65535 && NRC <= 65535;
-  static constexpr int TABW = D == 3 ? 2 : 1;  // 16-byte words per cube (8 + 1 or 4 + 1 indices)
+  // 2-D: one 16-byte word per cube (4 corners + atom slot).  3-D: a 16-byte word of corners per cube, then
+  // (structure of arrays, so that neither load has bank conflicts) one 32-bit atom slot per cube
   static constexpr int o_tab = ((o_y + (VGLOB ? 0 : NRHS * NDOF) + 1) / 2) * 2;
-  static constexpr int total = o_tab + (TAB ? N * TABW * 2 : 0);
+  static constexpr int o_tab_ro = o_tab + N * 2;  // 3-D only
+  // 3-D cells swept warp-slab-wise take 2x2x1 blocks of cubes per thread (elasticity_sweep_blocks)
+#ifndef HMX_NO_BLOCK_SWEEP
+  static constexpr bool BLK = D == 3 && TAB && !SUBW && (NM / 2) % WPR == 0;
+#else
+  static constexpr bool BLK = false;
+#endif
+  static constexpr int total = o_tab + (TAB ? N * 2 + (D == 3 ? (N + 1) / 2 : 0) : 0);
   static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
                 "block size must be NRHS * (a multiple or a divisor of 32)");
@@ -92,6 +100,206 @@ HMX_DEV void sym_inverse(const double* a, double* inv) {
     inv[3 % (D * (D + 1) / 2)] = (a00 * a22 - a02 * a02) * id;
     inv[4 % (D * (D + 1) / 2)] = (a01 * a02 - a00 * a12) * id;
     inv[5 % (D * (D + 1) / 2)] = (a00 * a11 - a01 * a01) * id;
+  }
+}
+
+// The T simplices of one cube: acc += K_cube u  (RHSMODE: acc += the load of the unit strain -E_q).
+// u, acc: [corner][component]; ro: the cube's atom slot.
+template <class CO, bool RHSMODE, int COLL, int NRC_>
+HMX_DEV void cube_apply(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms, int ro,
+                             const double (&u)[1 << CO::DIM][CO::DIM], double (&acc)[1 << CO::DIM][CO::DIM], int q,
+                             double sqrtw) {
+  constexpr int D = CO::DIM, T = kuhn_ntypes<D>(), NV = D * (D + 1) / 2, NA = CO::NATOMS, NA1 = NA > 0 ? NA : 1;
+  constexpr int NRC = NRC_, NC = 1 << D, CM = COLL & (NC - 1);
+#define HMX_MZ(p_, ax_) ((CO::MZERO >> ((p_)*D + (ax_))) & 1u)
+  HMX_UNROLL
+  for (int t = 0; t < T; ++t) {
+    double e[NV];
+    if (RHSMODE) {
+      HMX_UNROLL
+      for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -sqrtw : 0.0;
+    } else {
+      // e = sym(H) accumulated directly in engineering Voigt form,
+      // H[p][j] = sum_k Ms[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j]):  e[voigt(p,j)] += Ms[p][pi(k)] dk[j]
+      HMX_UNROLL
+      for (int v = 0; v < NV; ++v) e[v] = 0.0;
+      HMX_UNROLL
+      for (int k2 = 0; k2 < D; ++k2) {
+        const int ax = kuhn_axis<D>(t, k2);
+        if ((CM >> ax) & 1) continue;  // collapsed axis: the difference is identically zero
+        const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          const double dk = u[b1][j] - u[b0][j];
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p)
+            if (!HMX_MZ(p, ax)) {
+              // Voigt slot of the (p, j) entry: diagonal -> p, off-diagonal pairs in the order (0,1)[,(0,2),(1,2)]
+              const int lo = p < j ? p : j, hi = p < j ? j : p;
+              const int v = p == j ? p : D + (lo == 0 ? hi - 1 : 2);
+              e[v] += Ms[p * D + ax] * dk;
+            }
+        }
+      }
+    }
+    double sa[NA1], sig[NV];
+    HMX_UNROLL
+    for (int k2 = 0; k2 < NA1; ++k2) sa[k2] = NA > 0 ? s_atoms[(k2 * T + t) * NRC + ro] : 0.0;
+    CO::stress(pc, sa, e, sig);
+    double S[D][D];
+    HMX_UNROLL
+    for (int v = 0; v < D; ++v) S[v][v] = sig[v];
+    {
+      int v = D;
+      HMX_UNROLL
+      for (int r = 0; r < D; ++r)
+        HMX_UNROLL
+        for (int c = r + 1; c < D; ++c) {
+          S[r][c] = S[c][r] = sig[v];
+          ++v;
+        }
+    }
+    HMX_UNROLL
+    for (int k2 = 0; k2 < D; ++k2) {
+      const int ax = kuhn_axis<D>(t, k2);
+      if ((CM >> ax) & 1) continue;  // both ends are the same node: the two forces cancel
+      const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
+      // single-term columns (e.g. the rotation axis of C4's Jacobian) go straight into the two
+      // accumulators as FMAs; longer ones are summed once and added / subtracted
+      int nterms = 0;
+      HMX_UNROLL
+      for (int p = 0; p < D; ++p) nterms += HMX_MZ(p, ax) ? 0 : 1;
+      HMX_UNROLL
+      for (int j = 0; j < D; ++j) {
+        if (nterms == 1) {
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p)
+            if (!HMX_MZ(p, ax)) {
+              acc[b1][j] += S[j][p] * Ms[p * D + ax];
+              acc[b0][j] -= S[j][p] * Ms[p * D + ax];
+            }
+        } else {
+          double tk = 0.0;
+          HMX_UNROLL
+          for (int p = 0; p < D; ++p)
+            if (!HMX_MZ(p, ax)) tk += S[j][p] * Ms[p * D + ax];
+          acc[b1][j] += tk;
+          acc[b0][j] -= tk;
+        }
+      }
+    }
+  }
+#undef HMX_MZ
+}
+
+// entry `idx` of the per-cube index table (ElasticityLayout::TAB): corner node slots and atom slot
+template <int D>
+HMX_DEV void table_entry(const U4* s_tab, int ncubes, int idx, int (&node)[1 << D], int& ro) {
+  const U4 w0 = s_tab[idx];
+  const unsigned w[4] = {w0.x, w0.y, w0.z, w0.w};
+  HMX_UNROLL
+  for (int b = 0; b < (1 << D); ++b) node[b] = (int)((w[b >> 1] >> (16 * (b & 1))) & 0xffffu);
+  ro = D == 3 ? (int)reinterpret_cast<const unsigned*>(s_tab + ncubes)[idx] : (int)(w[2] & 0xffffu);
+}
+
+// Block sweep (3-D, SLAB scheme with the index table):  y += K p  with every thread taking a 2x2x1 BLOCK of cubes
+// per last-axis parity instead of one cube per colour.  The four cubes are visited in the order
+// A=(0,0) -> B=(1,0) -> C=(1,1) -> D=(0,1); the face shared by consecutive cubes keeps its displacements and its
+// partial forces in registers, so the block costs 20 node loads of p and 20 node updates of y where four separate
+// colours cost 32 + 32 (-37 % shared-memory traffic, the second ceiling of this kernel after the FP64 pipe).
+// A node is written back as soon as this thread has no further contribution to it.  Nodes shared with the
+// neighbouring blocks (block-local index 0 or 2 along x1 / x2; all of them belong to this warp, which owns whole
+// planes of the last axis) are updated in four phases FA..FD separated by __syncwarp: in one phase all threads
+// update the same block-local nodes, i.e. distinct nodes of the cell:
+//   FA: (0,0) and a first part of (0,1)   FB: (1,0), (2,0)   FC: (2,1), (2,2)   FD: (0,1), (1,1), (0,2), (1,2).
+template <class CO, int NM, int NT, int COLL, int VGLOB>
+HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
+                                     const double* s_p, double* s_y, int q, int l, double sqrtw, const U4* s_tab) {
+  using L = ElasticityLayout<CO, NM, NT, COLL, VGLOB>;
+  constexpr int D = 3, N = L::NP, NRC = L::NRC, NC = 8;
+  constexpr int HALF = NM / 2, TOT = HALF * HALF * HALF;  // cubes per colour
+  constexpr int SLABSZ = TOT / L::WPR;
+  static_assert(CO::DIM == 3 && COLL == 0 && NM % 2 == 0 && (NM / 2) % L::WPR == 0 && !L::SUBW && L::TAB, "block sweep");
+  const int wig = l >> 5, lig = l & 31;
+  const double* p_q = s_p + (size_t)q * D * N;
+  double* y_q = s_y + (size_t)q * D * N;
+  auto load = [&](double (&u)[NC][D], const int (&node)[NC], int mask, int val) {  // corners with (b & mask) == val
+    HMX_UNROLL
+    for (int b = 0; b < NC; ++b)
+      if ((b & mask) == val) {
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) u[b][j] = p_q[j * N + node[b]];
+      }
+  };
+  auto flush = [&](double (&acc)[NC][D], const int (&node)[NC], int mask, int val) {
+    HMX_UNROLL
+    for (int b = 0; b < NC; ++b)
+      if ((b & mask) == val) {
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          y_q[j * N + node[b]] += acc[b][j];
+          acc[b][j] = 0.0;
+        }
+      }
+  };
+  for (int cz = 0; cz < 2; ++cz) {
+    for (int k0 = wig * SLABSZ; k0 < (wig + 1) * SLABSZ; k0 += 32) {
+      const int k = k0 + lig;
+      const bool on = k < (wig + 1) * SLABSZ;
+      const int e0 = 4 * cz * TOT + (on ? k : k0);  // colour index = cx + 2 cy + 4 cz, TOT entries per colour
+      int node[NC], ro;
+      double u[NC][D], acc[NC][D], v[NC][D], bcc[NC][D];
+      // A = (cx, cy) = (0, 0)
+      table_entry<D>(s_tab, L::N, e0, node, ro);
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) acc[b][j] = 0.0;
+      load(u, node, 0, 0);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
+      if (on) flush(acc, node, 1, 0);  // FA: block-local (0,0) complete, (0,1) first part
+      // B = (1, 0): its x1 = 0 face is A's x1 = 1 face
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          v[b][j] = (b & 1) ? 0.0 : u[b | 1][j];
+          bcc[b][j] = (b & 1) ? 0.0 : acc[b | 1][j];
+        }
+      table_entry<D>(s_tab, L::N, e0 + TOT, node, ro);
+      load(v, node, 1, 1);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
+      warp_sync();
+      if (on) flush(bcc, node, 2, 0);  // FB: (1,0) and (2,0) complete
+      // C = (1, 1): its x2 = 0 face is B's x2 = 1 face
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          u[b][j] = (b & 2) ? 0.0 : v[b | 2][j];
+          acc[b][j] = (b & 2) ? 0.0 : bcc[b | 2][j];
+        }
+      table_entry<D>(s_tab, L::N, e0 + 3 * TOT, node, ro);
+      load(u, node, 2, 2);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
+      warp_sync();
+      if (on) flush(acc, node, 1, 1);  // FC: (2,1) and (2,2) complete
+      // D = (0, 1): its x1 = 1 face is C's x1 = 0 face
+      HMX_UNROLL
+      for (int b = 0; b < NC; ++b)
+        HMX_UNROLL
+        for (int j = 0; j < D; ++j) {
+          v[b][j] = (b & 1) ? u[b & ~1][j] : 0.0;
+          bcc[b][j] = (b & 1) ? acc[b & ~1][j] : 0.0;
+        }
+      table_entry<D>(s_tab, L::N, e0 + 2 * TOT, node, ro);
+      load(v, node, 1, 0);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
+      warp_sync();
+      if (on) flush(bcc, node, 0, 0);  // FD: (0,1), (1,1), (0,2), (1,2)
+      warp_sync();                     // next block of this warp / (with the group barrier) next parity
+    }
+    group_sync(1 + q, L::TPR);  // the other last-axis parity touches the neighbouring warps' planes
   }
 }
 
@@ -157,13 +365,7 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
       int node[NC];
       int ro;
       if (L::TAB) {
-        const U4* ent = s_tab + (size_t)(col * total + k) * L::TABW;
-        const U4 w0 = ent[0];
-        const unsigned w[8] = {w0.x, w0.y, w0.z, w0.w, D == 3 ? ent[L::TABW - 1].x : 0u, D == 3 ? ent[L::TABW - 1].y : 0u,
-                               D == 3 ? ent[L::TABW - 1].z : 0u, D == 3 ? ent[L::TABW - 1].w : 0u};
-        HMX_UNROLL
-        for (int b = 0; b < NC; ++b) node[b] = (int)((w[b >> 1] >> (16 * (b & 1))) & 0xffffu);
-        ro = (int)(w[NC >> 1] & 0xffffu);
+        table_entry<D>(s_tab, L::N, col * total + k, node, ro);
       } else {
         HMX_UNROLL
         for (int b = 0; b < NC; ++b) {
@@ -183,83 +385,7 @@ HMX_DEV void elasticity_sweep(const double* pc, const double (&Ms)[CO::DIM * CO:
           acc[b][j] = 0.0;
           u[b][j] = (RHSMODE || (b & CM)) ? 0.0 : s_p[(q * D + j) * N + node[b]];
         }
-      HMX_UNROLL
-      for (int t = 0; t < T; ++t) {
-        double e[NV];
-        if (RHSMODE) {
-          HMX_UNROLL
-          for (int v = 0; v < NV; ++v) e[v] = (v == q) ? -sqrtw : 0.0;
-        } else {
-          // e = sym(H) accumulated directly in engineering Voigt form,
-          // H[p][j] = sum_k Ms[p][pi(k)] * (u[P(k+1)][j] - u[P(k)][j]):  e[voigt(p,j)] += Ms[p][pi(k)] dk[j]
-          HMX_UNROLL
-          for (int v = 0; v < NV; ++v) e[v] = 0.0;
-          HMX_UNROLL
-          for (int k2 = 0; k2 < D; ++k2) {
-            const int ax = kuhn_axis<D>(t, k2);
-            if ((CM >> ax) & 1) continue;  // collapsed axis: the difference is identically zero
-            const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
-            HMX_UNROLL
-            for (int j = 0; j < D; ++j) {
-              const double dk = u[b1][j] - u[b0][j];
-              HMX_UNROLL
-              for (int p = 0; p < D; ++p)
-                if (!HMX_MZ(p, ax)) {
-                  // Voigt slot of the (p, j) entry: diagonal -> p, off-diagonal pairs in the order (0,1)[,(0,2),(1,2)]
-                  const int lo = p < j ? p : j, hi = p < j ? j : p;
-                  const int v = p == j ? p : D + (lo == 0 ? hi - 1 : 2);
-                  e[v] += Ms[p * D + ax] * dk;
-                }
-            }
-          }
-        }
-        double sa[NA1], sig[NV];
-        HMX_UNROLL
-        for (int k2 = 0; k2 < NA1; ++k2) sa[k2] = NA > 0 ? s_atoms[(k2 * T + t) * NRC + ro] : 0.0;
-        CO::stress(pc, sa, e, sig);
-        double S[D][D];
-        HMX_UNROLL
-        for (int v = 0; v < D; ++v) S[v][v] = sig[v];
-        {
-          int v = D;
-          HMX_UNROLL
-          for (int r = 0; r < D; ++r)
-            HMX_UNROLL
-            for (int c = r + 1; c < D; ++c) {
-              S[r][c] = S[c][r] = sig[v];
-              ++v;
-            }
-        }
-        HMX_UNROLL
-        for (int k2 = 0; k2 < D; ++k2) {
-          const int ax = kuhn_axis<D>(t, k2);
-          if ((CM >> ax) & 1) continue;  // both ends are the same node: the two forces cancel
-          const int b0 = kuhn_pmask<D>(t, k2) & ~CM, b1 = kuhn_pmask<D>(t, k2 + 1) & ~CM;
-          // single-term columns (e.g. the rotation axis of C4's Jacobian) go straight into the two
-          // accumulators as FMAs; longer ones are summed once and added / subtracted
-          int nterms = 0;
-          HMX_UNROLL
-          for (int p = 0; p < D; ++p) nterms += HMX_MZ(p, ax) ? 0 : 1;
-          HMX_UNROLL
-          for (int j = 0; j < D; ++j) {
-            if (nterms == 1) {
-              HMX_UNROLL
-              for (int p = 0; p < D; ++p)
-                if (!HMX_MZ(p, ax)) {
-                  acc[b1][j] += S[j][p] * Ms[p * D + ax];
-                  acc[b0][j] -= S[j][p] * Ms[p * D + ax];
-                }
-            } else {
-              double tk = 0.0;
-              HMX_UNROLL
-              for (int p = 0; p < D; ++p)
-                if (!HMX_MZ(p, ax)) tk += S[j][p] * Ms[p * D + ax];
-              acc[b1][j] += tk;
-              acc[b0][j] -= tk;
-            }
-          }
-        }
-      }
+      cube_apply<CO, RHSMODE, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
       HMX_UNROLL
       for (int b = 0; b < NC; ++b) {
         if (b & CM) continue;
@@ -334,8 +460,8 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         w[b >> 1] |= (unsigned)PG::index(cb) << (16 * (b & 1));
       }
       w[NC >> 1] |= (unsigned)AI::ridx(o);
-      s_tab[(size_t)idx * L::TABW] = U4{w[0], w[1], w[2], w[3]};
-      if (D == 3) s_tab[(size_t)idx * L::TABW + 1] = U4{w[4], w[5], w[6], w[7]};
+      s_tab[idx] = U4{w[0], w[1], w[2], w[3]};
+      if (D == 3) reinterpret_cast<unsigned*>(s_tab + L::N)[idx] = w[4];
     }
     sync();
   }
@@ -507,7 +633,10 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     while (L::SUBW ? warp_any(active && it < P.max_it) : (active && it < P.max_it)) {
       const bool mine = active && it < P.max_it;
       if (mine) ++it;
-      elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);  // y = K p
+      if constexpr (L::BLK)  // y = K p
+        elasticity_sweep_blocks<CO, NM, NT, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
+      else
+        elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
