@@ -72,6 +72,9 @@ struct ElasticityLayout {
 #else
   static constexpr bool BLK = false;
 #endif
+  // ... and when the blocks of one plane sit in one warp pass, the first contribution to a node of each sweep is
+  // a plain store: y needs no zeroing between the sweeps
+  static constexpr bool STORE1 = BLK && 32 % ((NM / 2) * (NM / 2)) == 0;
   static constexpr int total = o_tab + (TAB ? N * 2 + (D == 3 ? (N + 1) / 2 : 0) : 0);
   static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
@@ -231,18 +234,22 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
         for (int j = 0; j < D; ++j) u[b][j] = p_q[j * N + node[b]];
       }
   };
-  auto flush = [&](double (&acc)[NC][D], const int (&node)[NC], int mask, int val) {
+  // corners in `fresh` are the first contribution of the sweep to their node: stored, not added (L::STORE1)
+  auto flush = [&](double (&acc)[NC][D], const int (&node)[NC], int mask, int val, bool first, int fresh) {
     HMX_UNROLL
     for (int b = 0; b < NC; ++b)
       if ((b & mask) == val) {
         HMX_UNROLL
         for (int j = 0; j < D; ++j) {
-          y_q[j * N + node[b]] += acc[b][j];
+          double o = 0.0;
+          if (!(L::STORE1 && ((fresh >> b) & 1) && first)) o = y_q[j * N + node[b]];
+          y_q[j * N + node[b]] = o + acc[b][j];
           acc[b][j] = 0.0;
         }
       }
   };
   for (int cz = 0; cz < 2; ++cz) {
+    const bool first = cz == 0;  // parity 0 reaches every node of the cell
     for (int k0 = wig * SLABSZ; k0 < (wig + 1) * SLABSZ; k0 += 32) {
       const int k = k0 + lig;
       const bool on = k < (wig + 1) * SLABSZ;
@@ -257,7 +264,7 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
         for (int j = 0; j < D; ++j) acc[b][j] = 0.0;
       load(u, node, 0, 0);
       cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
-      if (on) flush(acc, node, 1, 0);  // FA: block-local (0,0) complete, (0,1) first part
+      if (on) flush(acc, node, 1, 0, first, 0x55);  // FA (all fresh): block-local (0,0) complete, (0,1) first part
       // B = (1, 0): its x1 = 0 face is A's x1 = 1 face
       HMX_UNROLL
       for (int b = 0; b < NC; ++b)
@@ -270,7 +277,7 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
       load(v, node, 1, 1);
       cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
       warp_sync();
-      if (on) flush(bcc, node, 2, 0);  // FB: (1,0) and (2,0) complete
+      if (on) flush(bcc, node, 2, 0, first, 0x11);  // FB ((1,0) fresh): (1,0) and (2,0) complete
       // C = (1, 1): its x2 = 0 face is B's x2 = 1 face
       HMX_UNROLL
       for (int b = 0; b < NC; ++b)
@@ -283,7 +290,7 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
       load(u, node, 2, 2);
       cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
       warp_sync();
-      if (on) flush(acc, node, 1, 1);  // FC: (2,1) and (2,2) complete
+      if (on) flush(acc, node, 1, 1, first, 0);  // FC: (2,1) and (2,2) complete
       // D = (0, 1): its x1 = 1 face is C's x1 = 0 face
       HMX_UNROLL
       for (int b = 0; b < NC; ++b)
@@ -296,7 +303,7 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
       load(v, node, 1, 0);
       cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
       warp_sync();
-      if (on) flush(bcc, node, 0, 0);  // FD: (0,1), (1,1), (0,2), (1,2)
+      if (on) flush(bcc, node, 0, 0, first, 0x22);  // FD ((1,1) fresh): (0,1), (1,1), (0,2), (1,2)
       warp_sync();                     // next block of this warp / (with the group barrier) next parity
     }
     group_sync(1 + q, L::TPR);  // the other last-axis parity touches the neighbouring warps' planes
@@ -658,7 +665,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
           for (int c = 0; c < D; ++c) {
             const int a = (q * D + c) * N + i;
             const double yv = s_y[a];
-            s_y[a] = 0.0;
+            if (!L::STORE1) s_y[a] = 0.0;
             r[c] = g_r[a];
             if (mine) {
               g_x[a] += alpha * s_p[a];
@@ -709,6 +716,17 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
+    if (L::STORE1) {  // the loop left y = K p behind
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) s_y[(q * D + c) * N + i] = 0.0;
+        }
+      }
+      group_barrier();
+    }
     elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
     sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {

@@ -59,6 +59,8 @@ CASES = [
     Case("e3_hooke_smooth_shear_n3", 3, 1, 3, "hooke_smooth_3d", "dtheta_shear_3d"),
     Case("e3_fibre_rot_n4", 3, 1, 4, "hooke_fibre_3d", "dtheta_rotation_3d"),
     Case("e3_cubic_shear_n4", 3, 1, 4, "cubic_3d", "dtheta_shear_3d"),  # anisotropic tensor, 3 atoms, all y axes
+    Case("e3_fibre_rot_n4_blocks", 3, 1, 4, "hooke_fibre_3d", "dtheta_rotation_3d", threads=192),  # 2x2x1 block sweep
+    Case("e3_hooke_smooth_shear_n6", 3, 1, 6, "hooke_smooth_3d", "dtheta_shear_3d"),  # block sweep, partial warp
     Case("e3_fibre_rot_n8_c4", 3, 1, 8, "hooke_fibre_3d", "dtheta_rotation_3d", heavy=True),  # BASELINE config 4
     Case("e3_fibre_rot_n10_l2", 3, 1, 10, "hooke_fibre_3d", "dtheta_rotation_3d", rtol=1e-9, heavy=True),  # vectors in L2
 ]
