@@ -212,9 +212,11 @@ HMX_DEV void table_entry(const U4* s_tab, int ncubes, int idx, int (&node)[1 << 
 // colours cost 32 + 32 (-37 % shared-memory traffic, the second ceiling of this kernel after the FP64 pipe).
 // A node is written back as soon as this thread has no further contribution to it.  Nodes shared with the
 // neighbouring blocks (block-local index 0 or 2 along x1 / x2; all of them belong to this warp, which owns whole
-// planes of the last axis) are updated in four phases FA..FD separated by __syncwarp: in one phase all threads
-// update the same block-local nodes, i.e. distinct nodes of the cell:
+// planes of the last axis) are updated in four phases FA..FD, one per cube, separated by __syncwarp: in one phase
+// all threads update the same block-local nodes, i.e. distinct nodes of the cell:
 //   FA: (0,0) and a first part of (0,1)   FB: (1,0), (2,0)   FC: (2,1), (2,2)   FD: (0,1), (1,1), (0,2), (1,2).
+// The old value of y is read at the START of its phase, straight into the accumulator the cube then adds to, and
+// the phase ends with plain stores: the read latency hides behind the cube's arithmetic and costs no register.
 template <class CO, int NM, int NT, int COLL, int VGLOB>
 HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms,
                                      const double* s_p, double* s_y, int q, int l, double sqrtw, const U4* s_tab) {
@@ -226,7 +228,8 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
   const int wig = l >> 5, lig = l & 31;
   const double* p_q = s_p + (size_t)q * D * N;
   double* y_q = s_y + (size_t)q * D * N;
-  auto load = [&](double (&u)[NC][D], const int (&node)[NC], int mask, int val) {  // corners with (b & mask) == val
+  // displacements of the corners with (b & mask) == val
+  auto load = [&](double (&u)[NC][D], const int (&node)[NC], int mask, int val) {
     HMX_UNROLL
     for (int b = 0; b < NC; ++b)
       if ((b & mask) == val) {
@@ -234,18 +237,26 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
         for (int j = 0; j < D; ++j) u[b][j] = p_q[j * N + node[b]];
       }
   };
-  // corners in `fresh` are the first contribution of the sweep to their node: stored, not added (L::STORE1)
-  auto flush = [&](double (&acc)[NC][D], const int (&node)[NC], int mask, int val, bool first, int fresh) {
+  // start of a phase: the corners (b & mask) == val are completed by this cube -> their accumulators take up the
+  // old y.  `carried` corners already hold the previous cube's part; `fresh` ones are the first contribution of
+  // the whole sweep to their node when `first` (L::STORE1): nothing to read
+  auto open = [&](double (&acc)[NC][D], const int (&node)[NC], int mask, int val, int carried, bool first, int fresh) {
+    HMX_UNROLL
+    for (int b = 0; b < NC; ++b) {
+      const bool sel = (b & mask) == val, car = (carried >> b) & 1;
+      HMX_UNROLL
+      for (int j = 0; j < D; ++j) {
+        if (!car) acc[b][j] = 0.0;
+        if (sel && !(L::STORE1 && ((fresh >> b) & 1) && first)) acc[b][j] += y_q[j * N + node[b]];
+      }
+    }
+  };
+  auto close = [&](const double (&acc)[NC][D], const int (&node)[NC], int mask, int val) {
     HMX_UNROLL
     for (int b = 0; b < NC; ++b)
       if ((b & mask) == val) {
         HMX_UNROLL
-        for (int j = 0; j < D; ++j) {
-          double o = 0.0;
-          if (!(L::STORE1 && ((fresh >> b) & 1) && first)) o = y_q[j * N + node[b]];
-          y_q[j * N + node[b]] = o + acc[b][j];
-          acc[b][j] = 0.0;
-        }
+        for (int j = 0; j < D; ++j) y_q[j * N + node[b]] = acc[b][j];
       }
   };
   for (int cz = 0; cz < 2; ++cz) {
@@ -254,57 +265,59 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
       const int k = k0 + lig;
       const bool on = k < (wig + 1) * SLABSZ;
       const int e0 = 4 * cz * TOT + (on ? k : k0);  // colour index = cx + 2 cy + 4 cz, TOT entries per colour
-      int node[NC], ro;
+      int node[NC], ro, node2[NC], ro2;
       double u[NC][D], acc[NC][D], v[NC][D], bcc[NC][D];
-      // A = (cx, cy) = (0, 0)
+      // A = (cx, cy) = (0, 0); completes its x1 = 0 face [(0,0), and (0,1) for now]
       table_entry<D>(s_tab, L::N, e0, node, ro);
-      HMX_UNROLL
-      for (int b = 0; b < NC; ++b)
-        HMX_UNROLL
-        for (int j = 0; j < D; ++j) acc[b][j] = 0.0;
       load(u, node, 0, 0);
+      open(acc, node, 1, 0, 0x00, first, 0x55);
+      table_entry<D>(s_tab, L::N, e0 + TOT, node2, ro2);
       cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
-      if (on) flush(acc, node, 1, 0, first, 0x55);  // FA (all fresh): block-local (0,0) complete, (0,1) first part
-      // B = (1, 0): its x1 = 0 face is A's x1 = 1 face
-      HMX_UNROLL
-      for (int b = 0; b < NC; ++b)
-        HMX_UNROLL
-        for (int j = 0; j < D; ++j) {
-          v[b][j] = (b & 1) ? 0.0 : u[b | 1][j];
-          bcc[b][j] = (b & 1) ? 0.0 : acc[b | 1][j];
-        }
-      table_entry<D>(s_tab, L::N, e0 + TOT, node, ro);
-      load(v, node, 1, 1);
-      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
+      load(v, node2, 1, 1);
+      if (on) close(acc, node, 1, 0);
       warp_sync();
-      if (on) flush(bcc, node, 2, 0, first, 0x11);  // FB ((1,0) fresh): (1,0) and (2,0) complete
-      // C = (1, 1): its x2 = 0 face is B's x2 = 1 face
+      // B = (1, 0): its x1 = 0 face is A's x1 = 1 face; completes its x2 = 0 face [(1,0), (2,0)]
       HMX_UNROLL
-      for (int b = 0; b < NC; ++b)
+      for (int b = 0; b < NC; b += 2)
         HMX_UNROLL
         for (int j = 0; j < D; ++j) {
-          u[b][j] = (b & 2) ? 0.0 : v[b | 2][j];
-          acc[b][j] = (b & 2) ? 0.0 : bcc[b | 2][j];
+          v[b][j] = u[b | 1][j];
+          bcc[b][j] = acc[b | 1][j];
         }
+      open(bcc, node2, 2, 0, 0x55, first, 0x11);
       table_entry<D>(s_tab, L::N, e0 + 3 * TOT, node, ro);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro2, v, bcc, q, sqrtw);
       load(u, node, 2, 2);
-      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
+      if (on) close(bcc, node2, 2, 0);
       warp_sync();
-      if (on) flush(acc, node, 1, 1, first, 0);  // FC: (2,1) and (2,2) complete
-      // D = (0, 1): its x1 = 1 face is C's x1 = 0 face
+      // C = (1, 1): its x2 = 0 face is B's x2 = 1 face; completes its x1 = 1 face [(2,1), (2,2)]
       HMX_UNROLL
       for (int b = 0; b < NC; ++b)
+        if (!(b & 2)) {
+          HMX_UNROLL
+          for (int j = 0; j < D; ++j) {
+            u[b][j] = v[b | 2][j];
+            acc[b][j] = bcc[b | 2][j];
+          }
+        }
+      open(acc, node, 1, 1, 0x33, first, 0);
+      table_entry<D>(s_tab, L::N, e0 + 2 * TOT, node2, ro2);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, u, acc, q, sqrtw);
+      load(v, node2, 1, 0);
+      if (on) close(acc, node, 1, 1);
+      warp_sync();
+      // D = (0, 1): its x1 = 1 face is C's x1 = 0 face; completes everything it touches [(0,1), (1,1), (0,2), (1,2)]
+      HMX_UNROLL
+      for (int b = 1; b < NC; b += 2)
         HMX_UNROLL
         for (int j = 0; j < D; ++j) {
-          v[b][j] = (b & 1) ? u[b & ~1][j] : 0.0;
-          bcc[b][j] = (b & 1) ? acc[b & ~1][j] : 0.0;
+          v[b][j] = u[b & ~1][j];
+          bcc[b][j] = acc[b & ~1][j];
         }
-      table_entry<D>(s_tab, L::N, e0 + 2 * TOT, node, ro);
-      load(v, node, 1, 0);
-      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro, v, bcc, q, sqrtw);
-      warp_sync();
-      if (on) flush(bcc, node, 0, 0, first, 0x22);  // FD ((1,1) fresh): (0,1), (1,1), (0,2), (1,2)
-      warp_sync();                     // next block of this warp / (with the group barrier) next parity
+      open(bcc, node2, 0, 0, 0xaa, first, 0x22);
+      cube_apply<CO, false, COLL, NRC>(pc, Ms, s_atoms, ro2, v, bcc, q, sqrtw);
+      if (on) close(bcc, node2, 0, 0);
+      warp_sync();  // next block of this warp / (with the group barrier) next parity
     }
     group_sync(1 + q, L::TPR);  // the other last-axis parity touches the neighbouring warps' planes
   }
