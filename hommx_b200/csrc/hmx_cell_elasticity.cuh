@@ -246,8 +246,12 @@ HMX_DEV void elasticity_sweep_blocks(const double* pc, const double (&Ms)[CO::DI
       const bool sel = (b & mask) == val, car = (carried >> b) & 1;
       HMX_UNROLL
       for (int j = 0; j < D; ++j) {
-        if (!car) acc[b][j] = 0.0;
-        if (sel && !(L::STORE1 && ((fresh >> b) & 1) && first)) acc[b][j] += y_q[j * N + node[b]];
+        const bool old_y = sel && !(L::STORE1 && ((fresh >> b) & 1) && first);
+        if (car) {
+          if (old_y) acc[b][j] += y_q[j * N + node[b]];
+        } else {
+          acc[b][j] = old_y ? y_q[j * N + node[b]] : 0.0;
+        }
       }
     }
   };

@@ -197,7 +197,13 @@ def _src_hash():
         if os.path.exists(p):
             with open(p, "rb") as f:
                 hsh.update(f.read())
+    hsh.update(" ".join(_extra_flags()).encode())
     return hsh.hexdigest()[:12]
+
+
+def _extra_flags():
+    """Extra nvcc flags for kernel experiments (``HMX_EXTRA_NVCC="-DHMX_NO_BLOCK_SWEEP"``); part of the cache key."""
+    return os.environ.get("HMX_EXTRA_NVCC", "").split()
 
 
 def default_min_blocks(dim, kind, n, threads):
@@ -264,7 +270,7 @@ def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_
         f.write(prog.source)
     tmp = cubin + f".tmp{os.getpid()}"
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I", CSRC,
-           *kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
+           *kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), *_extra_flags(), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
