@@ -187,6 +187,8 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
     if per <= 16 and nrhs % 2 == 0:
         return 16 * nrhs  # two right-hand sides share a warp (ElasticityLayout::SUBW)
     tpr = max(32, min(64, 32 * (-(-per // 32))))
+    if dim == 3 and coll == 0 and n % 2 == 0 and (n // 2) % (tpr // 32) != 0:
+        tpr = 32  # the 2x2x1 block sweep needs whole last-axis planes per warp (measured, n = 10: 4.7k -> 5.8k cells/s)
     return tpr * nrhs
 
 
@@ -206,12 +208,17 @@ def _extra_flags():
     return os.environ.get("HMX_EXTRA_NVCC", "").split()
 
 
-def default_min_blocks(dim, kind, n, threads):
+def default_min_blocks(dim, kind, n, threads, coll=0, vglob=0):
     """__launch_bounds__ minimum of resident CTAs per SM (caps registers per thread).  The Poisson
     kernels are latency-bound (few PCG iterations, ~25 barriers per point): two or more CTAs per SM
     hide it; 128 registers per thread still compile without spills."""
-    # (elasticity: only the small / axis-collapsed kernels have fewer than 384 threads; measured on the
-    # collapsed C4 kernel: 215k -> 276k cell solves/s going from 2 to 4-5 CTAs per SM)
+    if kind != POISSON and dim == 3 and coll == 0 and threads >= 32 * 6:
+        # full 3-D elasticity cells: the sweep wants 168 registers per thread (n = 6 at 192 threads, measured:
+        # 3 CTAs/SM at 96 registers 119k, 2 at 168 registers 183k, 1 at 254 registers 167k cell solves/s);
+        # with the vectors in L2 a second CTA only adds L2 contention (n = 10: 5.8k vs 4.5k)
+        return 1 if vglob else max(1, 65536 // (threads * 168))
+    # (elasticity: the small / axis-collapsed kernels; measured on the collapsed C4 kernel: 215k -> 276k cell
+    # solves/s going from 2 to 4-5 CTAs per SM)
     return max(1, min(8, 65536 // (threads * 112)))
 
 
@@ -252,7 +259,8 @@ def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False
     variant = default_variant(prog, n) if variant is None else variant
     coll = collapse_mask(prog, collapse) if variant == MATRIX_FREE else 0
     threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll)
-    min_blocks = min_blocks or default_min_blocks(prog.dim, prog.kind, n, threads)
+    vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
+    min_blocks = min_blocks or default_min_blocks(prog.dim, prog.kind, n, threads, coll, vg)
     return threads, min_blocks, variant, coll
 
 
