@@ -368,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
         return
     # CPU baseline: bounded sample on the host cores
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # rank 0 at N = 1 only (the other ranks' host cores idle otherwise)
         r, cores, sample = cpu_reference_rate(args.workload, 15.0)
         cpu = {"value": r, "unit": "cell solves/s", "cores": cores, "kind": "port", "sample": sample}
     line = {
