@@ -173,7 +173,8 @@ def test_empty_and_degenerate_inputs():
 
 @pytest.mark.parametrize("name,kw", [("p2_inclusion_n16", {}), ("p3_fulltensor_n6", {}), ("e3_fibre_rot_n8_c4", {}),
                                      ("e3_fibre_rot_n4", {"collapse": True}), ("e2_hooke_sin_n6", {}),
-                                     ("e3_fibre_rot_n4", {"variant": 1})])  # fmt: skip
+                                     ("e3_fibre_rot_n4", {"variant": 1}), ("e3_hooke_smooth_shear_n6", {}),
+                                     ("e3_fibre_rot_n10_l2", {})])  # fmt: skip
 def test_results_are_bitwise_reproducible(name, kw):
     """No atomics on the data path, fixed reduction orders, colour-ordered scatter: repeated runs and
     different grid sizes give bit-identical A_hom (compute-sanitizer is closed on this pool; a data race in
