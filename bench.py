@@ -353,13 +353,15 @@ def run_ours(args, rank, world, local_rank):
     # At N > 1 only the collapsed headline config is repeated (every rank takes part).
     other = {}
     if not args.no_extra:
-        todo = (("c2", False), ("c3", False), ("c4", True), ("c3", True), ("c2", True)) if world == 1 else ((args.workload, True),)
-        for name, collapse in todo:
+        # cell_solver "auto": small hard elasticity cells (the collapsed C4 cell) are factorised directly (K5)
+        todo = ((("c2", False, "auto"), ("c3", False, "auto"), ("c4", True, "auto"), ("c4", True, "pcg"), ("c3", True, "auto"),
+                 ("c2", True, "auto")) if world == 1 else ((args.workload, True, "auto"),))  # fmt: skip
+        for name, collapse, how in todo:
             if name == args.workload and not collapse:
                 continue
-            key = name + ("_axis_collapsed" if collapse else "")
+            key = name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "")
             try:
-                other[key] = quick_rate(name, local_rank, collapse, world)
+                other[key] = quick_rate(name, local_rank, collapse, world, how)
             except Exception as e:  # never lose the headline line
                 other[key] = {"error": str(e)[:200]}
     if rank != 0:
@@ -393,11 +395,11 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def quick_rate(name, device, collapse=False, world=1):
+def quick_rate(name, device, collapse=False, world=1, cell_solver="auto"):
     import torch
     import torch.distributed as dist
 
-    hmm = build_solver(name, world, collapse=collapse, device=device)
+    hmm = build_solver(name, world, collapse=collapse, device=device, cell_solver=cell_solver)
     hmm._ensure_solver()
     sol, d = hmm._solver, hmm._dev
     sol.set_stream(torch.cuda.current_stream().cuda_stream)
@@ -421,7 +423,8 @@ def quick_rate(name, device, collapse=False, world=1):
     note = ("micro axes the coefficient does not depend on solved on one layer of cubes (exact symmetry reduction, "
             "same A_hom to 1e-10; DESIGN.md 4)") if collapse else "full n^d micro cell"
     return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n_all, "n_gpus": world, "ms_per_step": best,
-            "cell_solves_per_s": n_all / (best * 1e-3), "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
+            "cell_solves_per_s": n_all / (best * 1e-3), "cell_solver": hmm.cell_solver_used,
+            "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
 
 
 def main():

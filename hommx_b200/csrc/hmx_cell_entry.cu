@@ -5,7 +5,7 @@
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
 #ifndef HMX_VARIANT
-#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator (barrier-staged), 2 = assembled, TMA-staged
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator (barrier-staged), 2 = assembled, TMA-staged, 3 = dense Cholesky
 #endif
 #if HMX_KIND == 0
 #include "hmx_cell_poisson.cuh"
@@ -13,6 +13,7 @@
 #include "hmx_cell_elasticity.cuh"
 #include "hmx_cell_elasticity_asm.cuh"
 #include "hmx_cell_elasticity_tma.cuh"
+#include "hmx_cell_dense.cuh"
 #endif
 #include HMX_COEFF_FILE
 
@@ -33,10 +34,12 @@ using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #elif HMX_VARIANT == 2
 using Layout = hmx::ElasticityTmaLayout<HMX_COEFF, HMX_NM, HMX_NT>;
+#elif HMX_VARIANT == 3
+using Layout = hmx::DenseLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
 #else
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #endif
-static_assert(HMX_VARIANT == 0 || HMX_COLL == 0, "the assembled variant has no collapsed form");
+static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled variant has no collapsed form");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
 constexpr int kSmemBytes = Layout::total * 8;
 constexpr int kScratch = Layout::scratch_doubles;
@@ -50,6 +53,8 @@ extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #elif HMX_VARIANT == 2
   hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 3
+  hmx::elasticity_dense_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
@@ -67,6 +72,8 @@ static void emu_body(void* arg) {
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #elif HMX_VARIANT == 2
   hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
+#elif HMX_VARIANT == 3
+  hmx::elasticity_dense_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif

@@ -104,6 +104,17 @@ HMX_DEV double fast_div(double a, double b) {
   r = fma(r, e, r);
   return a * r;
 }
+// 1 / sqrt(x) for finite x > 0: MUFU.RSQ64H seed + three Newton steps (quadratic: 2^-20 -> below 1 ulp)
+HMX_DEV double fast_rsqrt(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  HMX_UNROLL
+  for (int k = 0; k < 3; ++k) {
+    const double e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+  }
+  return r;
+}
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 }  // namespace hmx
 #endif

@@ -30,6 +30,9 @@ from . import assembly, codegen, fem, micro, native, parallel, quadrature
 from .mesh import as_simplex_mesh
 
 _CELL_OPTION_KEYS = {"ksp_rtol", "ksp_atol", "ksp_max_it"}
+# cell_solver="auto": mean PCG iterations per right-hand side (on a sample of macro cells) above which the small
+# elasticity cells are factorised directly instead (measured cross-over on B200: 15-40, scripts/probe_dense.py)
+DIRECT_ABOVE_ITERATIONS = 30
 
 
 def _triangle_area(points):
@@ -84,6 +87,7 @@ class BaseHMM:
         device=None,
         shard=True,
         collapse_invariant_axes=True,
+        cell_solver="auto",
     ):
         self._logger = logging.getLogger(__name__)
         self._msh = as_simplex_mesh(msh)
@@ -146,6 +150,12 @@ class BaseHMM:
         # exact symmetry reduction: micro axes the coefficient does not depend on are solved on one layer of
         # cubes (csrc/hmx_cell_common.cuh, Grid<.., COLL>); False solves the full n^d cell
         self._collapse = bool(collapse_invariant_axes)
+        # "pcg": the matrix-free PCG kernels; "direct": dense Cholesky per cell (elasticity cells of <= 192 unknowns,
+        # csrc/hmx_cell_dense.cuh); "auto": direct where the PCG iteration count of a sample of macro cells says it pays
+        if cell_solver not in ("auto", "pcg", "direct"):
+            raise ValueError("cell_solver must be 'auto', 'pcg' or 'direct'")
+        self._cell_solver = cell_solver
+        self.cell_solver_used = None
         self._shard = bool(shard)  # False: assemble every macro cell on this GPU even if torch.distributed is up
         self._solver = None
         self._dev = None
@@ -185,10 +195,15 @@ class BaseHMM:
         if dev is None:
             dev = torch.cuda.current_device()
         self._device = int(dev)
-        self._solver = native.CellSolver(
+        mk = lambda variant: native.CellSolver(  # noqa: E731
             self._program, self._structure.n, self._qp, self._qw, rtol=self._cell_rtol, atol=self._cell_atol,
-            max_it=self._cell_max_it, device=self._device, collapse=self._collapse,
+            max_it=self._cell_max_it, device=self._device, collapse=self._collapse, variant=variant,
         )  # fmt: skip
+        can_direct = native.dense_fits(self._program, self._structure.n, native.collapse_mask(self._program, self._collapse))
+        if self._cell_solver == "direct" and not can_direct:
+            raise native.HmxError(f"cell_solver='direct' holds at most {native.DENSE_MAX_DOF} unknowns per micro cell")
+        self._solver = mk(native.DENSE if self._cell_solver == "direct" else None)
+        self.cell_solver_used = "direct" if self._solver.variant == native.DENSE else "pcg"
         tdev = torch.device("cuda", self._device)
         n_cells = self._msh.num_cells
         lo, hi = assembly.shard_range(n_cells, self._rank, self._world)
@@ -210,6 +225,22 @@ class BaseHMM:
             d["halo"] = parallel.HaloExchange(d["shared"], torch.zeros(len(sh), dtype=torch.float64, device=tdev),
                                               self._solver.halo_pack_dev, self._solver.halo_unpack_dev)
         self._dev = d
+        if self._cell_solver == "auto" and can_direct and self.cell_solver_used == "pcg" and hi > lo:
+            # K5 "only where it beats CG": PCG iterations on a sample of this rank's macro cells decide (deterministic;
+            # measured cross-over on B200: 15-40 iterations for 48-192 unknowns, scripts/probe_dense.py)
+            m = min(hi - lo, 256)
+            self._solver.rhs_iterations(reset=True)
+            self._solver.assemble_macro_dev(m, d["cells"], self._msh.num_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"])
+            self._solver.sync()
+            mean_it = self._solver.rhs_iterations(reset=True) / (m * self._solver.m)
+            if mean_it > DIRECT_ABOVE_ITERATIONS:
+                self._solver.close()
+                self._solver = mk(native.DENSE)
+                self.cell_solver_used = "direct"
+                if self._world > 1:
+                    d["halo"] = parallel.HaloExchange(d["shared"], d["halo"].buf, self._solver.halo_pack_dev, self._solver.halo_unpack_dev)
+            self._logger.info("cell solver: %s (%.1f PCG iterations per right-hand side on %d sample cells)",
+                              self.cell_solver_used, mean_it, m)
 
     # ------------------------------------------------------------------ hot path
     def _assemble_stiffness(self):

@@ -27,8 +27,9 @@ KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh",
-            "hmx_cell_elasticity_asm.cuh", "hmx_cell_elasticity_tma.cuh", "hmx_cell_entry.cu")
-MATRIX_FREE, ASSEMBLED, ASSEMBLED_TMA = 0, 1, 2
+            "hmx_cell_elasticity_asm.cuh", "hmx_cell_elasticity_tma.cuh", "hmx_cell_dense.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, ASSEMBLED, ASSEMBLED_TMA, DENSE = 0, 1, 2, 3
+DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
 
 
@@ -151,14 +152,35 @@ def tma_fits(prog, n):
     return N % 32 == 0 and N <= 1024 and fixed + 2 * 8 * d * d * N <= SMEM_LIMIT
 
 
-def default_variant(prog, n):
-    """Elasticity: the matrix-free element kernel; the assembled (L2-streamed) variant is opt-in."""
+def dense_dofs(prog, n, coll=0):
+    d = prog.dim
+    return d * n ** (d - bin(coll & ((1 << d) - 1)).count("1"))
+
+
+def dense_fits(prog, n, coll=0):
+    """The direct (dense Cholesky) elasticity kernel: all unknowns of the cell in a 192 x 192 register tile."""
+    return prog.kind != POISSON and prog.dim + 1 <= dense_dofs(prog, n, coll) <= DENSE_MAX_DOF
+
+
+def default_variant(prog, n, collapse=False):
+    """Elasticity: the matrix-free element kernel; small cells (<= 192 unknowns, e.g. the axis-collapsed 8^3 cell
+    of BASELINE config 4) are factorised directly; the assembled (L2-streamed) variant is opt-in."""
     if prog.kind == POISSON:
         return MATRIX_FREE
+    forced = os.environ.get("HMX_ELASTICITY_VARIANT")
+    if forced == "matrix_free":
+        return MATRIX_FREE
+    if dense_fits(prog, n, collapse_mask(prog, collapse)) and (forced == "dense" or dense_default(prog, n, collapse)):
+        return DENSE
     fits = assembled_fits(prog, n)
     # measured on B200 (C4): the assembled variant reaches 33.4k cell solves/s against 36.4k of the
     # matrix-free kernel (L2 latency is not hidden by 16 warps at 128 registers) -> opt-in only
     return ASSEMBLED if (fits and os.environ.get("HMX_ELASTICITY_VARIANT") == "assembled") else MATRIX_FREE
+
+
+def dense_default(prog, n, collapse=False):
+    """Direct solve by default where it was measured faster than PCG (filled in from scripts/probe_dense.py)."""
+    return False
 
 
 def collapse_mask(prog, collapse=True):
@@ -171,6 +193,8 @@ def collapse_mask(prog, collapse=True):
 def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
     """Threads per CTA for the cell kernel of an n^dim micro mesh (minus its collapsed axes)."""
     N = n ** (dim - bin(coll).count("1"))
+    if kind != POISSON and variant == DENSE:
+        return 256  # 16 x 16 owners of the register tile
     if kind != POISSON and variant == ASSEMBLED:
         return max(64, 32 * (-(-N // 32)))  # one thread per node
     if kind != POISSON and variant == ASSEMBLED_TMA:
@@ -256,11 +280,13 @@ def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FR
 
 
 def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False):
-    variant = default_variant(prog, n) if variant is None else variant
-    coll = collapse_mask(prog, collapse) if variant == MATRIX_FREE else 0
+    variant = default_variant(prog, n, collapse) if variant is None else variant
+    coll = collapse_mask(prog, collapse) if variant in (MATRIX_FREE, DENSE) else 0
+    if variant == DENSE and not dense_fits(prog, n, coll):
+        raise HmxError(f"the dense variant holds at most {DENSE_MAX_DOF} unknowns per cell")
     threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll)
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
-    min_blocks = min_blocks or default_min_blocks(prog.dim, prog.kind, n, threads, coll, vg)
+    min_blocks = min_blocks or (1 if variant == DENSE else default_min_blocks(prog.dim, prog.kind, n, threads, coll, vg))
     return threads, min_blocks, variant, coll
 
 
@@ -309,7 +335,8 @@ class CellSolver:
         self._h = C.c_void_p()
         self.lib = load_library()
         image = kernel_image(prog, self.n, threads, min_blocks, variant, collapse)
-        self.collapse_mask = collapse_mask(prog, collapse)
+        self.variant = resolve(prog, self.n, threads, min_blocks, variant, collapse)[2]
+        self.collapse_mask = collapse_mask(prog, collapse) if self.variant in (MATRIX_FREE, DENSE) else 0
         self._image = C.create_string_buffer(image, len(image))
         qp = np.ascontiguousarray(qp, dtype=np.float64)
         qw = np.ascontiguousarray(qw, dtype=np.float64)

@@ -144,5 +144,6 @@ inline void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, MBar*
 inline void mbar_inval(MBar*) {}
 inline void fence_async_proxy() {}
 inline double fast_div(double a, double b) { return a / b; }
+inline double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 }  // namespace hmx

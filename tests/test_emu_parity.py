@@ -10,6 +10,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cpu_emu"))
 import cases as K  # noqa: E402
 import emu  # noqa: E402
+from hommx_b200 import native  # noqa: E402
 from oracle import hmm_oracle as ho  # noqa: E402
 
 LIGHT = [c for c in K.CASES if not c.heavy]
@@ -60,6 +61,45 @@ def test_assembled_elasticity_variant_matches_oracle(case):
     for k in range(len(x)):
         Ao = K.oracle_tensor(case, mic, x[k])
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+
+
+DENSE = [(c, co) for c in K.CASES if c.kind == 1 and c.threads is None for co in (False, True)
+         if native.dense_fits(K.program(c), c.n, native.collapse_mask(K.program(c), co))
+         and (not co or native.collapse_mask(K.program(c), True)) and (not c.heavy or co)]
+
+
+@pytest.mark.parametrize("case,collapse", DENSE, ids=[c.name + ("_collapsed" if co else "") for c, co in DENSE])
+def test_dense_cholesky_variant_matches_oracle(case, collapse):
+    """K5: the direct solve of small elasticity cells (csrc/hmx_cell_dense.cuh) -- odd and even n, 2-D and 3-D,
+    with and without collapsed axes, up to the 192 unknowns of the collapsed BASELINE config 4 cell."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, variant=native.DENSE, collapse=collapse, grid=2)
+    x = K.points(case, 3)
+    Ah, it, res = s.cell_tensors(x, return_stats=True)
+    assert np.all(it == 0) and np.all(res == 0.0)  # no iteration
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+
+
+@pytest.mark.parametrize("name,collapse", [("e2_hooke_sin_strat_n7", False), ("e3_fibre_rot_n4", True), ("e3_hooke_smooth_n4", False)])
+def test_dense_cholesky_correctors_and_local_matrices(name, collapse):
+    """The rare paths of the direct kernel: back substitution for the correctors, fused local macro matrices."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    ref = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-12, collapse=collapse)
+    s = emu.EmuSolver(prog, case.n, qp, qw, variant=native.DENSE, collapse=collapse)
+    x = K.points(case, 1)
+    a, b = s.correctors(x)[0], ref.correctors(x)[0]
+    ax = tuple(range(2, a.ndim))
+    a, b = a - a.mean(axis=ax, keepdims=True), b - b.mean(axis=ax, keepdims=True)
+    assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max() + 1e-14
+    cells, xyz = K.random_simplices(case.dim, 3)
+    S, Sr = s.local_matrices(cells, xyz)[0], ref.local_matrices(cells, xyz)[0]
+    assert np.abs(S - Sr).max() <= 1e-10 * np.abs(Sr).max()
 
 
 @pytest.mark.parametrize("name", ["p2_fulltensor_strat_n9", "p3_fulltensor_shear_n5", "e2_hooke_sin_strat_n7", "e3_hooke_smooth_n4"])

@@ -149,6 +149,40 @@ def test_elasticity_stratified_fibres_match_oracle():
     assert st["macro_cells"] == m.num_cells and st["cell_kernel_ms"] > 0 and st["rhs_iterations"] >= s.cell_iterations.sum()
 
 
+def test_cell_solver_choice_direct_vs_pcg():
+    """K5 behind the drop-in classes: BASELINE config 4's micro cell (8^3, fibre along y0 -> collapsed to 192
+    unknowns, ~220 PCG iterations) is factorised directly under cell_solver="auto"; "pcg" and "direct" give the
+    same macro matrix to 1e-10; an easy coefficient stays on PCG."""
+    m = mesh.create_box((0, 0, 0), (1.0, 0.4, 0.1), (4, 2, 1))
+    f = lambda x: pufl.as_vector([0.0, 0.0, -0.05 * 0.4**2])  # noqa: E731
+    mk = lambda how, n=8, coeff=Cf.hooke_fibre_3d: LinearElasticityStratifiedHMM(  # noqa: E731
+        m, coeff(pufl), f, mesh.create_unit_cube(n, n, n), 0.01, Cf.dtheta_rotation_3d(pufl),
+        petsc_options_cell_problem=TIGHT, cell_solver=how)
+    mats = {}
+    for how in ("pcg", "direct", "auto"):
+        s = mk(how)
+        s._assemble_stiffness()
+        mats[how] = sp_values(s)
+        assert s.cell_solver_used == ("pcg" if how == "pcg" else "direct")
+        assert (s.cell_iterations.max() == 0) == (how != "pcg")
+    ref = np.abs(mats["pcg"]).max()
+    assert np.abs(mats["direct"] - mats["pcg"]).max() <= 1e-10 * ref
+    assert np.array_equal(mats["auto"], mats["direct"])
+    easy = mk("auto", 4, Cf.hooke_smooth_3d)
+    easy._assemble_stiffness()
+    assert easy.cell_solver_used == "pcg"
+    with pytest.raises(ValueError):
+        mk("lu")
+    big = LinearElasticityStratifiedHMM(m, Cf.hooke_fibre_3d(pufl), f, mesh.create_unit_cube(8, 8, 8), 0.01, Cf.dtheta_rotation_3d(pufl),
+                                        collapse_invariant_axes=False, cell_solver="direct")  # fmt: skip
+    with pytest.raises(Exception):
+        big._assemble_stiffness()  # 1,536 unknowns do not fit the direct kernel: loud, no fallback
+
+
+def sp_values(s):
+    return np.array(s._dev["vals"].cpu().numpy(), copy=True)
+
+
 def test_hmm_equals_periodic_homogenisation():
     """test/integration/test_integration_poisson.py:188-240: for A = A(y) PoissonHMM and PoissonPeriodicHMM
     agree: macro matrices (Frobenius < 1e-8) and solutions (L2 < 1e-12 in the reference, with LU)."""

@@ -52,6 +52,41 @@ def test_local_matrix_matches_oracle(name):
     s.close()
 
 
+DENSE = [(c, co) for c in ALL if c.kind == 1 and c.threads is None for co in (False, True)
+         if native.dense_fits(K.program(c), c.n, native.collapse_mask(K.program(c), co))
+         and (not co or native.collapse_mask(K.program(c), True))]
+
+
+@pytest.mark.parametrize("case,collapse", DENSE, ids=[c.name + ("_collapsed" if co else "") for c, co in DENSE])
+def test_dense_cholesky_variant_matches_oracle(case, collapse):
+    """K5: small elasticity cells factorised directly (csrc/hmx_cell_dense.cuh), incl. the 192-unknown collapsed
+    cell of BASELINE config 4: A_hom against the oracle, local matrices and correctors against the PCG kernel."""
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, variant=native.DENSE, collapse=collapse)
+    assert s.variant == native.DENSE
+    x = K.points(case, 4)
+    Ah, it, res = s.cell_tensors(x, return_stats=True)
+    assert np.all(it == 0) and np.all(res == 0.0)
+    mic = K.oracle_cell(case, prog)
+    for k in range(len(x)):
+        Ao = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    ref = native.CellSolver(prog, case.n, qp, qw, rtol=1e-12, collapse=collapse, variant=native.MATRIX_FREE)
+    cells, xyz = K.random_simplices(case.dim, 5)
+    nb2 = s.nb * s.nb
+    gp = np.arange(len(cells) * nb2 + 1, dtype=np.int64)
+    gs = np.arange(len(cells) * nb2, dtype=np.int32)
+    S, Sr = s.assemble_macro(cells, xyz, gp, gs, want_local=True)[1], ref.assemble_macro(cells, xyz, gp, gs, want_local=True)[1]
+    assert np.abs(S - Sr).max() <= 1e-10 * np.abs(Sr).max()
+    a, b = s.cell_correctors(x[:1])[0], ref.cell_correctors(x[:1])[0]
+    ax = tuple(range(2, a.ndim))
+    a, b = a - a.mean(axis=ax, keepdims=True), b - b.mean(axis=ax, keepdims=True)
+    assert np.abs(a - b).max() <= 1e-8 * np.abs(b).max() + 1e-14
+    s.close()
+    ref.close()
+
+
 ELAST = [c for c in ALL if c.kind == 1 and native.assembled_fits(K.program(c), c.n)]
 
 
@@ -174,7 +209,8 @@ def test_empty_and_degenerate_inputs():
 @pytest.mark.parametrize("name,kw", [("p2_inclusion_n16", {}), ("p3_fulltensor_n6", {}), ("e3_fibre_rot_n8_c4", {}),
                                      ("e3_fibre_rot_n4", {"collapse": True}), ("e2_hooke_sin_n6", {}),
                                      ("e3_fibre_rot_n4", {"variant": 1}), ("e3_hooke_smooth_shear_n6", {}),
-                                     ("e3_fibre_rot_n10_l2", {})])  # fmt: skip
+                                     ("e3_fibre_rot_n10_l2", {}), ("e3_fibre_rot_n8_c4", {"collapse": True, "variant": 3}),
+                                     ("e3_cubic_shear_n4", {"variant": 3})])  # fmt: skip
 def test_results_are_bitwise_reproducible(name, kw):
     """No atomics on the data path, fixed reduction orders, colour-ordered scatter: repeated runs and
     different grid sizes give bit-identical A_hom (compute-sanitizer is closed on this pool; a data race in
