@@ -235,10 +235,9 @@ HMX_DEV void block_sum(double (&v)[NV], double* buf) {
 // with C[:,i] the gradient (Poisson) or engineering-Voigt strain (elasticity, unrolled
 // dof i = a*D + k, hmm.py:31-40) of macro basis function i  (SURVEY.md A.3).
 template <int D, int KIND>
-HMX_DEV void macro_element_matrix(const double* verts /* (D+1) x 3 */, const double* Ahom, double* S) {
+HMX_DEV double macro_strain_matrix(const double* verts /* (D+1) x 3 */,
+                                   double (&C)[KIND == 0 ? D : D * (D + 1) / 2][KIND == 0 ? D + 1 : (D + 1) * D]) {
   constexpr int NV = D + 1;
-  constexpr int MV = KIND == 0 ? D : D * (D + 1) / 2;
-  constexpr int NB = KIND == 0 ? NV : NV * D;
   double J[D][D];  // columns are edge vectors
   HMX_UNROLL
   for (int r = 0; r < D; ++r)
@@ -281,7 +280,6 @@ HMX_DEV void macro_element_matrix(const double* verts /* (D+1) x 3 */, const dou
     }
     G[p][0] = -s;
   }
-  double C[MV][NB];
   if (KIND == 0) {
     HMX_UNROLL
     for (int p = 0; p < D; ++p)
@@ -305,6 +303,15 @@ HMX_DEV void macro_element_matrix(const double* verts /* (D+1) x 3 */, const dou
           }
       }
   }
+  return vol;
+}
+
+template <int D, int KIND>
+HMX_DEV void macro_element_matrix(const double* verts /* (D+1) x 3 */, const double* Ahom, double* S) {
+  constexpr int MV = KIND == 0 ? D : D * (D + 1) / 2;
+  constexpr int NB = KIND == 0 ? D + 1 : (D + 1) * D;
+  double C[MV][NB];
+  const double vol = macro_strain_matrix<D, KIND>(verts, C);
   for (int i = 0; i < NB; ++i)
     for (int j = 0; j < NB; ++j) {
       double s = 0.0;

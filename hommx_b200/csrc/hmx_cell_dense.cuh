@@ -53,7 +53,8 @@ struct DenseLayout {
   static constexpr int o_b = o_yb + 2 * NRHS;              // [NRHS][NPAD] loads, later y = L^-1 b
   static constexpr int o_gram = o_b + NRHS * NPAD;         // [NRHS][NRHS]
   static constexpr int o_dsave = o_gram + NRHS * NRHS;     // [NPAD] 1 / L_kk (corrector path)
-  static constexpr int o_tri = o_dsave + NPAD;             // packed lower triangle, by columns
+  static constexpr int o_epi = o_dsave + NPAD;             // A_hom [NRHS][NRHS], macro strain matrix [NV][(D+1) D], |T|
+  static constexpr int o_tri = o_epi + NRHS * NRHS + NV * (D + 1) * D + 2;  // packed lower triangle, by columns
   static constexpr int total = o_tri + NTRI;
   static constexpr int scratch_doubles = 8;                // none needed
   static_assert(NT == TG * TG, "the dense kernel runs 256 threads");
@@ -382,21 +383,40 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
       }
     }
 
-    // ---- 5. A_hom = <C> - y^T y, local macro matrix ----
+    // ---- 5. A_hom = <C> - y^T y, local macro matrix (one thread per entry: with one CTA per SM nothing else
+    //         would hide a serial epilogue) ----
+    constexpr int NB = (D + 1) * D;
+    double* s_ah = sm + L::o_epi;            // [NRHS][NRHS]
+    double* s_cm = s_ah + NRHS * NRHS;       // [NV][NB] macro strain matrix, then |T|
     if (t_id == 0) {
-      double Ah[NRHS * NRHS];
       for (int qq = 0; qq < NRHS; ++qq) {
         double e[NV], sg[NV];
         HMX_UNROLL
         for (int v = 0; v < NV; ++v) e[v] = (v == qq) ? 1.0 : 0.0;
         CO::stress(pc, smean, e, sg);
-        for (int p = 0; p < NRHS; ++p) Ah[p * NRHS + qq] = sg[p] - s_gram[p * NRHS + qq];
+        for (int p = 0; p < NRHS; ++p) s_ah[p * NRHS + qq] = sg[p] - s_gram[p * NRHS + qq];
       }
-      if (P.A_hom != nullptr)
-        for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
-      if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
+      if (P.S_loc != nullptr) {
+        double Cm[NV][NB];
+        s_cm[NV * NB] = macro_strain_matrix<D, 1>(verts, Cm);
+        HMX_UNROLL
+        for (int p = 0; p < NV; ++p)
+          HMX_UNROLL
+          for (int i = 0; i < NB; ++i) s_cm[p * NB + i] = Cm[p][i];
+      }
       if (P.iters != nullptr) P.iters[pt] = 0;  // direct solve
       if (P.resid != nullptr) P.resid[pt] = 0.0;
+    }
+    sync();
+    if (P.A_hom != nullptr && t_id < NRHS * NRHS) P.A_hom[pt * NRHS * NRHS + t_id] = s_ah[t_id];
+    if (P.S_loc != nullptr && t_id < NB * NB) {
+      const int i = t_id / NB, j = t_id - i * NB;
+      double acc = 0.0;  // same summation order as macro_element_matrix
+      HMX_UNROLL
+      for (int p = 0; p < NV; ++p)
+        HMX_UNROLL
+        for (int q2 = 0; q2 < NV; ++q2) acc += s_cm[p * NB + j] * s_ah[p * NRHS + q2] * s_cm[q2 * NB + i];
+      P.S_loc[pt * NB * NB + t_id] = s_cm[NV * NB] * acc;
     }
     sync();  // shared memory is reused by the next macro point
   }
