@@ -10,7 +10,7 @@ import pytest
 import scipy.sparse as sp
 
 import coefficients as Cf
-from hommx_b200 import PoissonHMM, PoissonStratifiedHMM, assembly, fem, mesh, micro, native
+from hommx_b200 import LinearElasticityStratifiedHMM, PoissonHMM, PoissonStratifiedHMM, assembly, fem, mesh, micro, native
 from hommx_b200 import ufl as pufl
 from oracle import hmm_oracle as ho
 from oracle import meshes as omesh
@@ -113,6 +113,28 @@ def test_constructor_checks_and_default_boundary_condition():
     assert s.function_space.num_dofs == 16
     s2 = PoissonStratifiedHMM(m2, A, lambda x: 1.0, mesh.create_unit_square(4, 4), 0.1, Cf.dtheta_wavy(pufl))
     assert s2._bcs == []  # hmm.py:670-757: no default condition
+
+
+def test_kernel_choice_for_elasticity_cells():
+    """Host side of K5 and of the block sweep: which kernel variant / launch shape a cell gets."""
+    import cases as K
+
+    c4 = K.program(K.BY_NAME["e3_fibre_rot_n8_c4"])
+    assert native.collapse_mask(c4, True) == 1  # the fibre runs along y0
+    assert not native.dense_fits(c4, 8, 0) and native.dense_fits(c4, 8, 1)  # 1,536 vs 192 unknowns
+    assert native.resolve(c4, 8, variant=native.DENSE, collapse=True) == (256, 1, native.DENSE, 1)
+    with pytest.raises(native.HmxError, match="192"):
+        native.resolve(c4, 8, variant=native.DENSE)  # loud, no fallback
+    assert native.resolve(c4, 8)[:3] == (384, 1, native.MATRIX_FREE)  # PCG stays the default variant
+    # full 3-D cells: threads chosen so that every warp owns whole planes of the last axis (block sweep)
+    assert native.default_threads(3, 1, 8) == 384 and native.default_threads(3, 1, 10) == 192 and native.default_threads(3, 1, 12) == 384
+    assert native.resolve(c4, 6)[:2] == (192, 2) and native.resolve(c4, 10)[:2] == (192, 1)
+    poisson = K.program(K.BY_NAME["p2_smooth_n8"])
+    assert not native.dense_fits(poisson, 8)
+    m3 = mesh.create_unit_cube(2, 2, 2)
+    with pytest.raises(ValueError, match="cell_solver"):
+        LinearElasticityStratifiedHMM(m3, Cf.hooke_fibre_3d(pufl), lambda x: pufl.as_vector([0.0, 0.0, 1.0]), mesh.create_unit_cube(4, 4, 4),
+                                      0.1, Cf.dtheta_rotation_3d(pufl), cell_solver="lu")  # fmt: skip
 
 
 def test_micro_structure_detection():
