@@ -63,6 +63,7 @@ def main():
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_sweep_c5.md"))
     ap.add_argument("--max-points", type=int, default=1000000)
     ap.add_argument("--budget-ms", type=float, default=1500.0, help="skip larger point counts once a launch exceeds this")
+    ap.add_argument("--only", default="", help="run only the families whose label contains this text")
     args = ap.parse_args()
     peak, _ = native.measure_peaks(0)
     lines = [
@@ -76,6 +77,8 @@ def main():
     ]
     rng = np.random.default_rng(0)
     for f in FAMILIES:
+        if args.only not in f[0]:
+            continue
         prog = program(f)
         for n in f[5]:
             if not fits(prog, n):
