@@ -40,7 +40,7 @@ def build(prog, n, threads=None, variant=None, collapse=False):
         with open(coeff, "w") as f:
             f.write(prog.source)
         cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DHMX_EMULATE", "-I", HERE, "-I", native.CSRC,
-               *native.kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), "-x", "c++", os.path.join(native.CSRC, "hmx_cell_entry.cu"),
+               *native.kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), *native._extra_flags(), "-x", "c++", os.path.join(native.CSRC, "hmx_cell_entry.cu"),
                "-o", so + ".tmp", "-lpthread"]  # fmt: skip
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
