@@ -22,11 +22,11 @@ def _barycentres(msh):
     return np.ascontiguousarray(msh.x[msh.cells].mean(axis=1))
 
 
-def _solver(name, collapse=False, rtol=1e-9):
+def _solver(name, collapse=False, rtol=1e-9, variant=None):
     case = K.BY_NAME[name]
     prog = K.program(case)
     qp, qw = K.tables(case, prog)
-    return native.CellSolver(prog, case.n, qp, qw, rtol=rtol, collapse=collapse)
+    return native.CellSolver(prog, case.n, qp, qw, rtol=rtol, collapse=collapse, variant=variant)
 
 
 def _spd(A, tol=1e-10):
@@ -99,7 +99,7 @@ def test_c3_poisson_3d_full_size():
 
 def test_c4_rotated_fibres_throughput_size():
     """configs[3] at the bench size: 40x16x4 hexahedra -> 15,360 macro cells, 8^3 micro cell, 6 right-hand
-    sides.  Full cell (block sweep) against the axis-collapsed kernel, tensor symmetries, rigid-body null
+    sides.  Full cell (block sweep) against the axis-collapsed PCG kernel and the direct (dense Cholesky) kernel, tensor symmetries, rigid-body null
     space of the 12x12 local matrices, equal rotation angle -> identical bits."""
     msh = mesh.create_box((0.0, 0.0, 0.0), (1.0, 0.4, 0.1), (40, 16, 4))
     x = _barycentres(msh)
@@ -110,6 +110,10 @@ def test_c4_rotated_fibres_throughput_size():
     assert res.max() <= 1e-9 and it.max() < 1000
     _spd(A)
     assert np.abs(A - Ac).max() <= 1e-10 * np.abs(A).max()
+    direct = _solver("e3_fibre_rot_n8_c4", collapse=True, variant=native.DENSE)  # K5: a third, direct kernel
+    Ad = direct.cell_tensors(x)
+    assert np.abs(Ad - A).max() <= 1e-10 * np.abs(A).max() and np.abs(Ad - Ac).max() <= 1e-10 * np.abs(A).max()
+    direct.close()
     # the coefficient sees the macro point through the angle gamma(x1) only
     order = np.lexsort((x[:, 2], x[:, 0], x[:, 1]))
     xs, As = x[order], A[order]
