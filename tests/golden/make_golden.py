@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import cases as K  # noqa: E402
 
 NAMES = ["p2_smooth_n16_c1", "p2_laminate_wavy_n32_c2", "p3_smooth_n8_c3", "p2_inclusion_n16", "p2_fulltensor_strat_n9",
-         "p3_fulltensor_shear_n5", "e2_hooke_sin_strat_n7", "e3_hooke_smooth_shear_n3", "e3_fibre_rot_n4", "e3_fibre_rot_n8_c4"]  # fmt: skip
+         "p3_fulltensor_shear_n5", "e2_hooke_sin_strat_n7", "e3_hooke_smooth_shear_n3", "e3_fibre_rot_n4", "e3_fibre_rot_n8_c4",
+         "e3_hooke_smooth_shear_n6", "e3_cubic_shear_n4"]  # fmt: skip
 
 
 def main():

@@ -35,3 +35,24 @@ def test_cuda_matches_golden_vectors(name, collapse):
     for k, A in enumerate(GOLD[name]["A_hom"]):
         assert np.abs(Ah[k] - np.array(A)).max() <= 1e-10 * np.abs(np.array(A)).max()
     s.close()
+
+
+DIRECT = [(n, co) for n in GOLD for co in (False, True) if K.BY_NAME[n].kind == 1 and K.BY_NAME[n].threads is None]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,collapse", DIRECT)
+def test_direct_kernel_matches_golden_vectors(name, collapse):
+    """K5 (dense Cholesky per cell) against the committed vectors, wherever the cell fits its 192 unknowns."""
+    from hommx_b200 import native
+
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    if not native.dense_fits(prog, case.n, native.collapse_mask(prog, collapse)):
+        pytest.skip("more than 192 unknowns: PCG only")
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, variant=native.DENSE, collapse=collapse)
+    Ah = s.cell_tensors(np.array(GOLD[name]["x"]))
+    for k, A in enumerate(GOLD[name]["A_hom"]):
+        assert np.abs(Ah[k] - np.array(A)).max() <= 1e-10 * np.abs(np.array(A)).max()
+    s.close()
