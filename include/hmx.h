@@ -49,7 +49,10 @@ typedef struct hmx_desc {
   int32_t nq;        /* quadrature points per micro element */
   const double* qp;  /* [T][nq][dim] points per element type, cube-local, units of h (T = dim!) */
   const double* qw;  /* [nq] weights, normalised to sum 1 */
-  const void* kernel_image; /* cubin/fatbin of the cell kernel specialised for the coefficient */
+  const void* kernel_image; /* cubin/fatbin of the cell kernel specialised for the coefficient, the micro mesh size and
+                             * the solver variant (matrix-free PCG, or the direct dense-Cholesky kernel for elasticity
+                             * cells of <= 192 unknowns).  The direct kernel ignores rtol / atol /
+                             * max_it and reports 0 iterations. */
   size_t kernel_image_size;
   double rtol;       /* PCG: stop at sqrt(r.z) <= max(rtol*sqrt(r0.z0), atol) (ksp_rtol / ksp_atol) */
   double atol;
