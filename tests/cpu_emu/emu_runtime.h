@@ -66,10 +66,30 @@ inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, voi
     s.ctx[t].uc_link = &s.main_ctx;
     makecontext(&s.ctx[t], fiber_entry, 0);
   }
+  // Scheduling order of the fibers between barriers.  A kernel without data races gives bit-identical results
+  // under every order (tests/test_emu_parity.py::test_results_do_not_depend_on_the_thread_schedule):
+  //   HMX_EMU_ORDER unset / "forward": 0, 1, 2, ...   "reverse": n-1, ..., 0   "shuffle:<seed>": a new random
+  //   permutation in every round
+  const char* mode = std::getenv("HMX_EMU_ORDER");
+  const bool reverse = mode != nullptr && std::strcmp(mode, "reverse") == 0;
+  const bool shuffle = mode != nullptr && std::strncmp(mode, "shuffle", 7) == 0;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull ^ (shuffle && mode[7] == ':' ? std::strtoull(mode + 8, nullptr, 10) : 0ull) ^
+                           ((unsigned long long)bid << 32);
+  std::vector<int> order(nthreads);
+  for (int t = 0; t < nthreads; ++t) order[t] = reverse ? nthreads - 1 - t : t;
   bool alive = true;
   while (alive) {
     alive = false;
-    for (int t = 0; t < nthreads; ++t) {
+    if (shuffle)
+      for (int t = nthreads - 1; t > 0; --t) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        const int r = (int)((rng >> 33) % (unsigned long long)(t + 1));
+        const int tmp = order[t];
+        order[t] = order[r];
+        order[r] = tmp;
+      }
+    for (int k = 0; k < nthreads; ++k) {
+      const int t = order[k];
       if (s.done[t]) continue;
       cta.cur = t;
       swapcontext(&s.main_ctx, &s.ctx[t]);

@@ -187,3 +187,31 @@ def test_vectors_in_l2_fallback_matches_oracle(name, monkeypatch):
     for k in range(len(x)):
         Ao = K.oracle_tensor(case, mic, x[k])
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+
+
+SCHED = [("p2_smooth_n8", {}), ("p3_smooth_n4", {}), ("p2_inclusion_n16", {}), ("e2_hooke_sin_n6", {}), ("e3_fibre_rot_n4", {}),
+         ("e3_fibre_rot_n4", {"collapse": True}), ("e3_fibre_rot_n4_blocks", {}), ("e3_hooke_smooth_shear_n6", {}),
+         ("e3_hooke_smooth_n4", {"variant": native.DENSE}), ("e2_hooke_sin_strat_n7", {"variant": native.DENSE}),
+         ("e3_fibre_rot_n4", {"variant": 1}), ("e3_fibre_rot_n4", {"variant": 2})]  # fmt: skip
+
+
+@pytest.mark.parametrize("name,kw", SCHED, ids=[n + "".join(f"_{k}{v}" for k, v in kw.items()) for n, kw in SCHED])
+def test_results_do_not_depend_on_the_thread_schedule(name, kw, monkeypatch):
+    """CPU-side race check: the emulator runs the fibers of a CTA between barriers in forward, reverse and random
+    order (tests/cpu_emu/emu_runtime.h, HMX_EMU_ORDER).  Any read of a location another thread writes in the
+    same barrier interval -- a data race on the device -- makes the result depend on that order; the kernels
+    are deterministic, so the tensors, correctors and iteration counts must be bit-identical."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-9, threads=case.threads, grid=2, **kw)
+    x = K.points(case, 3, seed=7)
+    ref = None
+    for order in ("forward", "reverse", "shuffle:1", "shuffle:2"):
+        monkeypatch.setenv("HMX_EMU_ORDER", order)
+        got = (s.cell_tensors(x, return_stats=True), s.correctors(x[:1]))
+        if ref is None:
+            ref = got
+            continue
+        assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[0][1], ref[0][1]), order
+        assert np.array_equal(got[1], ref[1]), order
