@@ -60,7 +60,11 @@ HMX_HOSTDEV constexpr int kuhn_pmask(int t, int a) {
   return m;
 }
 
-HMX_HOSTDEV constexpr int ipow(int b, int e) { return e <= 0 ? 1 : b * ipow(b, e - 1); }
+HMX_HOSTDEV constexpr int ipow(int b, int e) {  // (a loop: a recursive device function has no static stack bound)
+  int r = 1;
+  for (int k = 0; k < e; ++k) r *= b;
+  return r;
+}
 HMX_HOSTDEV constexpr int popcount3(int m) { return (m & 1) + ((m >> 1) & 1) + ((m >> 2) & 1); }
 HMX_HOSTDEV constexpr int sym_index(int D, int i, int j) {  // upper triangle, row major
   return i <= j ? i * D - i * (i - 1) / 2 + (j - i) : j * D - j * (j - 1) / 2 + (i - j);

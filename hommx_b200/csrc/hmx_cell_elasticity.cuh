@@ -24,6 +24,7 @@
 //   A_hom[p][q] = <C>[p][q] - b_p.x_q - x_p.r_q.
 #pragma once
 #include "hmx_cell_common.cuh"
+#include "hmx_cell_coarse.cuh"
 
 namespace hmx {
 
@@ -75,7 +76,13 @@ struct ElasticityLayout {
   // ... and when the blocks of one plane sit in one warp pass, the first contribution to a node of each sweep is
   // a plain store: y needs no zeroing between the sweeps
   static constexpr bool STORE1 = BLK && 32 % ((NM / 2) * (NM / 2)) == 0;
-  static constexpr int total = o_tab + (TAB ? N * 2 + (D == 3 ? (N + 1) / 2 : 0) : 0);
+  // two-level preconditioner (hmx_cell_coarse.cuh): inverse coarse matrix, parent table, one column buffer
+  using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB>;
+  static constexpr int o_ei = o_tab + (TAB ? N * 2 + (D == 3 ? (N + 1) / 2 : 0) : 0);  // [NTRI] packed lower triangle
+  static constexpr int o_par = o_ei + (CS::ON ? CS::NTRI : 0);                           // [NP] 2 x 16-bit level-1 slots
+  static constexpr int o_cbuf = o_par + (CS::ON ? (NP + 1) / 2 : 0);                     // [CS::CBUF]
+  static constexpr int total = o_cbuf + (CS::ON ? CS::CBUF : 0);
+  static_assert(!CS::ON || (CS::setup_doubles <= 2 * NRHS * NDOF && !SUBW), "coarse set-up scratch must fit in the p / y area");
   static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
                 "block size must be NRHS * (a multiple or a divisor of 32)");
@@ -453,6 +460,11 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   U4* s_tab = reinterpret_cast<U4*>(sm + L::o_tab);
   double* s_p = VGLOB ? g_r + NRHS * NDOF : sm + L::o_p;  // VGLOB: "s_" vectors are in the L2 scratch too
   double* s_y = VGLOB ? g_r + 2 * NRHS * NDOF : sm + L::o_y;
+  using CS = typename L::CS;
+  constexpr bool TWO = CS::ON;  // additive two-level preconditioner (hmx_cell_coarse.cuh)
+  double* s_ei = sm + L::o_ei;
+  unsigned* s_par = reinterpret_cast<unsigned*>(sm + L::o_par);
+  double* s_cbuf = sm + L::o_cbuf;
 
   const int t_id = tid();
   const int q = t_id / TPR, l = t_id - q * TPR;
@@ -463,6 +475,9 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
   const double sqrtw = sqrt(vol);
   int red_flip = 0;
 
+  if (TWO) {  // level-1 parents of every fine node slot: depends on the micro grid only
+    for (int i = t_id; i < N; i += NT) s_par[i] = coarse_parents<CS, PG>(i);
+  }
   if (L::TAB) {
     // the cube -> (corner node slots, atom slot) table depends on the micro grid only: built once per launch.
     // Entry order = sweep order: colour (last-axis parity slowest), then the cube index inside the colour.
@@ -525,7 +540,8 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         for (int k = 0; k < NA; ++k) s_atoms[(k * T + t) * NRC + rc] = acc[k];
       }
     }
-    for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;  // the accumulation target
+    if (!TWO)
+      for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;  // the accumulation target
     sync();
 
     // ---- 2. atom means, block-Jacobi preconditioner ----
@@ -600,6 +616,11 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       HMX_UNROLL
       for (int k = 0; k < NSYM; ++k) s_dinv[k * N + i] = inv[k];
     }
+    if constexpr (TWO) {
+      // coarse Galerkin matrix of this point, inverted (uses the p / y area as scratch)
+      coarse_setup<CO, NM, NT, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_ei, s_cbuf, s_red, L::NSLOT * L::NREDV, red_flip);
+      for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;  // the accumulation target
+    }
     sync();  // the preconditioner is complete before any group starts
 
     // ---- 3./4. one PCG per right-hand side, each group on its own named barrier ----
@@ -623,7 +644,90 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     };
     elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);  // y = b_q
     double rz, rz0;
-    {
+    // z = M^-1 r at node slot i of this right-hand side (two-level: r sits in y_q, the level-1 coarse solution in
+    // its class-0 slots, where the residual of those nodes is taken from the scratch instead)
+    // OWN: thread l of a right-hand side owns level-1 node l and the 2^D fine nodes 2 c(l) + bits(j), j = its node
+    // index (TPR = number of level-1 nodes, e.g. the 8^3 cell with 64 threads per right-hand side): the parents of
+    // its nodes are c(l) and c(l) + bits(j) -- no table look-up, the first parent is loaded once
+    constexpr bool OWN = TWO && TPR == CS::NC1 && NPT == (1 << D);
+    int own_lo[D], own_hi[D];  // slot offsets of c(l) and of c(l) + 1 along every axis
+    if (OWN) {
+      int rr = l;
+      HMX_UNROLL
+      for (int a = 0; a < D; ++a) {
+        const int ca = rr % CS::H;
+        rr /= CS::H;
+        own_lo[a] = ca * CS::stride1(a);
+        own_hi[a] = ((ca + 1) % CS::H) * CS::stride1(a);
+      }
+    }
+    auto precond_node = [&](int i, int j, double (&r)[D], double (&z)[D]) {
+      HMX_UNROLL
+      for (int c = 0; c < D; ++c) r[c] = (TWO && i >= CS::NC1) ? s_y[(q * D + c) * N + i] : g_r[(q * D + c) * N + i];
+      int ia = 0, ib = 0;
+      if (OWN) {
+        ia = l;
+        HMX_UNROLL
+        for (int a = 0; a < D; ++a) ib += ((j >> a) & 1) ? own_hi[a] : own_lo[a];
+      } else if (TWO) {
+        const unsigned par = s_par[i];
+        ia = (int)(par & 0xffffu);
+        ib = (int)(par >> 16);
+      }
+      HMX_UNROLL
+      for (int c = 0; c < D; ++c) {
+        double zz = 0.0;
+        HMX_UNROLL
+        for (int c2 = 0; c2 < D; ++c2) zz += s_dinv[sym_index(D, c, c2) * N + i] * r[c2];
+        if (TWO) zz += 0.5 * (s_y[(q * D + c) * N + ia] + s_y[(q * D + c) * N + ib]);
+        z[c] = zz;
+      }
+    };
+    if constexpr (TWO) {
+      double splus[D];  // OWN: r[2c] + 1/2 sum of this thread's other nodes = its half of the level-1 restriction
+      HMX_UNROLL
+      for (int c = 0; c < D; ++c) splus[c] = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            const double rr = s_y[(q * D + c) * N + i];  // r = b stays in y for the restriction
+            g_r[(q * D + c) * N + i] = rr;
+            g_x[(q * D + c) * N + i] = 0.0;
+            if (OWN) splus[c] += j == 0 ? rr : 0.5 * rr;
+          }
+        }
+      }
+      coarse_correct<CO, NM, NT, COLL, VGLOB, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
+      double part = 0.0;
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          double r[D], z[D];
+          precond_node(i, j, r, z);
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            part += r[c] * z[c];
+            s_p[(q * D + c) * N + i] = z[c];
+          }
+        }
+      }
+      if (!L::STORE1) {  // the sweep accumulates into y: clear it once nobody reads the coarse solution any more
+        group_sync(1 + q, TPR);
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = l + j * TPR;
+          if (i < N) {
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) s_y[(q * D + c) * N + i] = 0.0;
+          }
+        }
+      }
+      rz = rz0 = group_sum(part);  // its barrier also publishes p (and the cleared y)
+    } else {
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -672,6 +776,80 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       }
       const double pAp = group_sum(part);
       const double alpha = (mine && pAp > 0.0) ? fast_div(rz, pAp) : 0.0;
+      if constexpr (TWO) {
+        // x += alpha p, r -= alpha K p; r goes to the scratch and, for the restriction, into y
+        double splus[D];
+        HMX_UNROLL
+        for (int c = 0; c < D; ++c) splus[c] = 0.0;
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = l + j * TPR;
+          if (i < N) {
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) {
+              const int a = (q * D + c) * N + i;
+              const double rr = g_r[a] - alpha * s_y[a];
+              g_x[a] += alpha * s_p[a];
+              g_r[a] = rr;
+              s_y[a] = rr;
+              if (OWN) splus[c] += j == 0 ? rr : 0.5 * rr;
+            }
+          }
+        }
+        coarse_correct<CO, NM, NT, COLL, VGLOB, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
+        // z = M^-1 r overwrites r in y (the class-0 slots hold the coarse solution other threads still read: the z
+        // of those nodes -- at most NKEEP per thread -- waits in registers)
+        constexpr int NKEEP = (CS::NC1 + TPR - 1) / TPR;
+        double zk[NKEEP][D];
+        part = 0.0;
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j) {
+          const int i = l + j * TPR;
+          if (i < N) {
+            double r[D], z[D];
+            precond_node(i, j, r, z);
+            HMX_UNROLL
+            for (int c = 0; c < D; ++c) {
+              part += r[c] * z[c];
+              if (j < NKEEP && i < CS::NC1)
+                zk[j < NKEEP ? j : 0][c] = z[c];
+              else
+                s_y[(q * D + c) * N + i] = z[c];
+            }
+          }
+        }
+        const double rz_new = group_sum(part);
+        const double beta = fast_div(rz_new, rz);
+        rz = rz_new;
+        if (!(rz_new > tol2)) active = false;
+        if (active) {
+          HMX_UNROLL
+          for (int j = 0; j < NPT; ++j) {
+            const int i = l + j * TPR;
+            if (i < N) {
+              HMX_UNROLL
+              for (int c = 0; c < D; ++c) {
+                const int a = (q * D + c) * N + i;
+                const double z = (j < NKEEP && i < CS::NC1) ? zk[j < NKEEP ? j : 0][c] : s_y[a];
+                s_p[a] = z + beta * s_p[a];
+              }
+            }
+          }
+          if (!L::STORE1) {  // clear y for the next sweep once nobody reads the coarse solution any more
+            group_barrier();
+            HMX_UNROLL
+            for (int j = 0; j < NPT; ++j) {
+              const int i = l + j * TPR;
+              if (i < N) {
+                HMX_UNROLL
+                for (int c = 0; c < D; ++c) s_y[(q * D + c) * N + i] = 0.0;
+              }
+            }
+          }
+          group_barrier();  // publish p (and the cleared y) to the group
+        }
+        continue;
+      }
       part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -733,7 +911,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
 
     // ---- 5. epilogue: b -> y again, A_hom = <C> - b_p.x_q - x_p.r_q ----
-    if (L::STORE1) {  // the loop left y = K p behind
+    if (L::STORE1 || TWO) {  // the loop left y = K p (two-level: the residual and the coarse solution) behind
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
         const int i = l + j * TPR;

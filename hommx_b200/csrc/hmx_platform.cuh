@@ -51,6 +51,8 @@ HMX_DEV double seg_sum(double v, int width) {
   for (int m = width >> 1; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
   return v;
 }
+// value of lane (lane ^ m) of the warp: SHFL.BFLY; every lane of the warp calls it
+HMX_DEV double lane_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 HMX_DEV bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 // ---- mbarrier + bulk async copy (TMA 1-D): the producer/consumer pipeline of the TMA-staged kernel ----
 // An MBar occupies HMX_MBAR_BYTES of shared memory (8 used on the device; the CPU emulation needs more).

@@ -26,7 +26,7 @@ INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-_HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_elasticity.cuh",
+_HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_coarse.cuh", "hmx_cell_elasticity.cuh",
             "hmx_cell_elasticity_asm.cuh", "hmx_cell_elasticity_tma.cuh", "hmx_cell_dense.cuh", "hmx_cell_entry.cu")
 MATRIX_FREE, ASSEMBLED, ASSEMBLED_TMA, DENSE = 0, 1, 2, 3
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
@@ -267,16 +267,26 @@ def vectors_in_l2(prog, n, coll=0):
     return 1 if need > SMEM_LIMIT else 0
 
 
+def precond_mode(prog, variant=MATRIX_FREE):
+    """1: the matrix-free elasticity kernel is built with the additive two-level preconditioner (block Jacobi + an
+    exactly inverted Galerkin coarse matrix, csrc/hmx_cell_coarse.cuh) wherever its coarse space fits next to the
+    vectors (the kernel decides: ``CoarseSpace::ON``); 0: block Jacobi only (``HMX_PRECOND=jacobi``)."""
+    if prog.kind == POISSON or variant != MATRIX_FREE:
+        return 0
+    return 0 if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" else 1
+
+
 def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE, coll=0):
     kind = "p" if prog.kind == POISSON else "e"
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
-    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}g{vg}_{prog.key}_{_src_hash()}"
+    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}g{vg}p{precond_mode(prog, variant)}_{prog.key}_{_src_hash()}"
 
 
 def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE, coll=0):
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
     return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}",
-            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}", f"-DHMX_VGLOB={vg}"]  # fmt: skip
+            f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}", f"-DHMX_VGLOB={vg}",
+            f"-DHMX_PRECOND={precond_mode(prog, variant)}"]  # fmt: skip
 
 
 def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False):

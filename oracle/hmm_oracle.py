@@ -84,7 +84,9 @@ class MicroCell:
     ``kind``: 'poisson' (bs=1) or 'elasticity' (bs=d).
     """
 
-    def __init__(self, mesh, kind, degree):
+    def __init__(self, mesh, kind, degree, rule=None):
+        """``rule`` = (points (nq, d), weights (nq,)) on the reference simplex overrides the table of ``degree``
+        (e.g. ``basix.make_quadrature`` output dumped by tests/golden/make_reference_golden.py)."""
         self.mesh = mesh
         self.kind = kind
         d = self.d = mesh.dim
@@ -99,7 +101,7 @@ class MicroCell:
         g[:, 1:, :] = Jinv
         g[:, 0, :] = -Jinv.sum(axis=1)
         self.grad = g
-        qp, qw = simplex_rule(d, degree)
+        qp, qw = simplex_rule(d, degree) if rule is None else (np.asarray(rule[0], float), np.asarray(rule[1], float))
         self.qw = qw / qw.sum()  # normalised: element mean
         yq = v[:, :1, :] + np.einsum("eij,qj->eqi", J, qp)  # (ne, nq, d)
         self.yq = yq

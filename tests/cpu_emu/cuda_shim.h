@@ -93,6 +93,14 @@ inline double seg_sum(double v, int width) {
   }
   return t[me & 31];
 }
+inline double lane_xor(double v, int m) {
+  emu::Cta* c = emu::g_cta;
+  const int me = c->cur, par = c->wpar[me];
+  c->wbuf[par * c->nthreads + me] = v;
+  c->wpar[me] = par ^ 1;
+  barrier(16 + me / 32, 32);
+  return c->wbuf[par * c->nthreads + (me / 32) * 32 + ((me & 31) ^ m)];
+}
 inline bool warp_any(bool p) {
   emu::Cta* c = emu::g_cta;
   const int me = c->cur, par = c->wpar[me];

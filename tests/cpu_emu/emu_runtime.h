@@ -45,7 +45,15 @@ inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, voi
   cta.cur = 0;
   std::memset(cta.arrived, 0, sizeof cta.arrived);
   std::memset(cta.gen, 0, sizeof cta.gen);
-  std::vector<double> smem(smem_doubles + 2, 0.0), wbuf(2 * nthreads, 0.0);
+  // shared memory is NOT zero-initialised on the device: HMX_EMU_POISON=1 fills it with NaNs (0xfff7... bit
+  // patterns, huge as integers) so that a read of a slot nobody wrote shows up as a NaN result or a wild index
+  const char* poison = std::getenv("HMX_EMU_POISON");
+  double fill = 0.0;
+  if (poison && poison[0] == '1') {
+    const unsigned long long bits = 0xfff7dead7ff7beefULL;
+    std::memcpy(&fill, &bits, sizeof fill);
+  }
+  std::vector<double> smem(smem_doubles + 2, fill), wbuf(2 * nthreads, 0.0);
   std::vector<int> wpar(nthreads, 0);
   cta.smem = smem.data();
   cta.wbuf = wbuf.data();
