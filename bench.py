@@ -9,7 +9,9 @@ into the macro CSR values and -- when cells are sharded over GPUs -- the sum of 
 Default workload: BASELINE.json configs[3], the one the north-star target is quoted on
 (LinearElasticityStratifiedHMM, rotated-fibre beam [0,1]x[0,0.4]x[0,0.1], 8^3 micro cell, 6
 right-hand sides per point).  ``--workload c1|c2|c3`` select the Poisson configs.  Per-GPU work
-is fixed as N grows (weak scaling): the macro mesh gets N slabs of cells.
+is fixed as N grows (weak scaling): the macro mesh gets N slabs of cells; ``--scaling strong``
+keeps the named mesh size (C4 80x32x8, C3 32^3) at every N, and every run reports those
+strong-scaling wall times under ``other_workloads`` (``*_strong``).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -29,69 +31,25 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-import coefficients as Cf  # noqa: E402  (tests/coefficients.py: the reference's example coefficients)
+from hommx_b200 import workloads as W  # noqa: E402  (the reference's example problems, BASELINE configs[0..3])
 
-# ---------------------------------------------------------------------------------------------
-# workloads
-# ---------------------------------------------------------------------------------------------
-WORKLOADS = {
-    # name: class, dim, micro n, coefficient, Dtheta, per-GPU macro mesh (slab count multiplies the last axis)
-    "c4": dict(cls="LinearElasticityStratifiedHMM", dim=3, kind=1, n=8, coeff="hooke_fibre_3d", dtheta="dtheta_rotation_3d",
-               box=((0.0, 0.0, 0.0), (1.0, 0.4, 0.1)), cells=(40, 16, 4), eps=0.01,
-               desc="BASELINE configs[3]: rotated-fibre beam, Hooke mu=100/0.001 lambda=1, 8^3 micro cell, 6 RHS/point"),
-    "c3": dict(cls="PoissonHMM", dim=3, kind=0, n=8, coeff="smooth_sin", dtheta=None,
-               box=((0.0, 0.0, 0.0), (1.0, 1.0, 1.0)), cells=(32, 32, 32), eps=2.0**-3,
-               desc="BASELINE configs[2]: PoissonHMM 3D, 32^3 macro mesh per GPU, 8^3 micro cell"),
-    "c2": dict(cls="PoissonStratifiedHMM", dim=2, kind=0, n=32, coeff="laminate", dtheta="dtheta_wavy",
-               box=((0.0, 0.0), (1.0, 1.0)), cells=(256, 256), eps=1e-5,
-               desc="BASELINE configs[1]: PoissonStratifiedHMM wavy laminate, 256x256 macro mesh per GPU, 32x32 micro cell"),
-    "c1": dict(cls="PoissonHMM", dim=2, kind=0, n=16, coeff="smooth_sin", dtheta=None,
-               box=((0.0, 0.0), (1.0, 1.0)), cells=(32, 32), eps=2.0**-5,
-               desc="BASELINE configs[0]: PoissonHMM 2D, 32x32 macro mesh, 16x16 micro cell"),
-}  # fmt: skip
+WORKLOADS = W.WORKLOADS
 CELL_RTOL, CELL_ATOL = 1e-8, 1e-10
-
-
 SHRINK = 1
+SCALING = "weak"
+REF_SAMPLE = 256  # macro cells of the CPU arm's fixed sample
 
 
 def build_solver(wl, world, collapse=False, **kw):
-    import hommx_b200 as hx
-    from hommx_b200 import mesh
-    from hommx_b200 import ufl as pufl
-
-    w = WORKLOADS[wl]
-    cells = [max(1, c // SHRINK) for c in w["cells"]]
-    cells[-1] *= world
-    msh = mesh.create_rectangle(*w["box"], cells) if w["dim"] == 2 else mesh.create_box(*w["box"], cells)
-    mic = mesh.create_unit_square(w["n"], w["n"]) if w["dim"] == 2 else mesh.create_unit_cube(w["n"], w["n"], w["n"])
-    A = getattr(Cf, w["coeff"])(pufl)
-    f = (lambda x: 1.0) if w["kind"] == 0 else (lambda x: pufl.as_vector([0.0] * (w["dim"] - 1) + [-0.05 * 0.4**2]))
-    opts = {"ksp_rtol": CELL_RTOL, "ksp_atol": CELL_ATOL}
-    cls = getattr(hx, w["cls"])
-    if w["dtheta"]:
-        return cls(msh, A, f, mic, w["eps"], getattr(Cf, w["dtheta"])(pufl), petsc_options_cell_problem=opts,
-                   collapse_invariant_axes=collapse, **kw)
-    return cls(msh, A, f, mic, w["eps"], petsc_options_cell_problem=opts, collapse_invariant_axes=collapse, **kw)
+    return W.build_solver(wl, world, collapse=collapse, shrink=SHRINK, scaling=SCALING, rtol=CELL_RTOL, atol=CELL_ATOL, **kw)
 
 
 def kernel_jobs():
     """Cell kernels the bench needs (compiled by __graft_entry__.build())."""
-    from hommx_b200 import codegen
-    from hommx_b200 import ufl as pufl
-
-    jobs = []
-    for w in WORKLOADS.values():
-        A = getattr(Cf, w["coeff"])(pufl)
-        Dt = getattr(Cf, w["dtheta"])(pufl) if w["dtheta"] else None
-        prog = codegen.build_program(A, w["dim"], w["kind"], Dt)
-        jobs.append((prog, w["n"], None))
-        jobs.append((prog, w["n"], None, False, True, None, None, True))  # axis-collapsed variant (other_workloads)
-    return jobs
+    return W.kernel_jobs()
 
 
 def algorithmic_flops(w, n_pts, rhs_iterations):
@@ -113,20 +71,20 @@ def _oracle_worker(args):
     wl, idx = args
     from oracle import hmm_oracle as ho
     from oracle import meshes as omesh
-    from oracle import npufl
+    from oracle import npufl, ufldegree
 
     w = WORKLOADS[wl]
     n = w["n"]
     state = _oracle_worker.__dict__.setdefault("state", {})
     if wl not in state:
         mm = omesh.create_unit_square(n, n) if w["dim"] == 2 else omesh.create_unit_cube(n, n, n)
-        degree = {"smooth_sin": 3}.get(w["coeff"], 0)
+        degree = ufldegree.form_degree(W.coefficient(wl, ufldegree)[0], w["dim"])
         macro = omesh.create_rectangle(*w["box"], list(w["cells"])) if w["dim"] == 2 else omesh.create_box(*w["box"], list(w["cells"]))
+        A, Dn = W.coefficient(wl, npufl)
         Dt = None
-        if w["dtheta"]:
-            Dn = getattr(Cf, w["dtheta"])(npufl)
+        if Dn is not None:
             Dt = lambda x: np.asarray(Dn(np.asarray(x, float)))[..., 0]  # noqa: E731
-        state[wl] = (ho.MicroCell(mm, "poisson" if w["kind"] == 0 else "elasticity", degree), macro, getattr(Cf, w["coeff"])(npufl), Dt)
+        state[wl] = (ho.MicroCell(mm, "poisson" if w["kind"] == 0 else "elasticity", degree), macro, A, Dt)
     mic, macro, A, Dt = state[wl]
     out = []
     for c in idx:
@@ -135,26 +93,37 @@ def _oracle_worker(args):
     return len(out)
 
 
-def cpu_reference_rate(wl, budget_s, procs=None):
-    """macro cells/s of the restated reference algorithm on `procs` host cores over a bounded sample."""
-    import multiprocessing as mp
+class CpuArm:
+    """The restated reference algorithm (oracle, kind "port") on all host cores over a FIXED sample of macro cells:
+    drawn once with a fixed seed, the same cells every step, split evenly over the worker processes."""
 
-    procs = procs or (os.cpu_count() or 1)
-    w = WORKLOADS[wl]
-    n_total = int(np.prod(w["cells"])) * (2 if w["dim"] == 2 else 6)
-    rng = np.random.default_rng(0)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(procs) as pool:
-        # calibrate on one cell per process (also builds the per-process micro cell once)
+    def __init__(self, wl, n_sample=REF_SAMPLE, procs=None):
+        import multiprocessing as mp
+
+        self.wl, self.procs = wl, procs or (os.cpu_count() or 1)
+        w = WORKLOADS[wl]
+        n_total = int(np.prod(w["cells"])) * (2 if w["dim"] == 2 else 6)
+        n_sample = max(self.procs, min(n_sample, n_total))
+        cells = np.random.default_rng(0).choice(n_total, size=n_sample, replace=False)
+        self.chunks = [(wl, [int(c) for c in cells[p :: self.procs]]) for p in range(self.procs)]
+        self.n_sample = n_sample
+        self.pool = mp.get_context("fork").Pool(self.procs)
+        self.pool.map(_oracle_worker, [(wl, [int(cells[0])])] * self.procs)  # builds the micro cell once per process
+
+    def step(self):
+        """cells/s of one pass over the sample"""
         t0 = time.perf_counter()
-        pool.map(_oracle_worker, [(wl, [int(c)]) for c in rng.integers(0, n_total, procs)])
-        t1 = time.perf_counter() - t0
-        per_proc = max(1, int(budget_s / max(t1, 1e-3)))
-        chunks = [(wl, [int(c) for c in rng.integers(0, n_total, per_proc)]) for _ in range(procs)]
-        t0 = time.perf_counter()
-        done = sum(pool.map(_oracle_worker, chunks))
-        dt = time.perf_counter() - t0
-    return done / dt, procs, f"{done} macro cells of {wl} drawn at random, literal n_b-corrector algorithm (sparse LU), {dt:.1f} s"
+        done = sum(self.pool.map(_oracle_worker, self.chunks))
+        return done / (time.perf_counter() - t0)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+    def sample(self, rates):
+        spread = (max(rates) - min(rates)) / np.mean(rates) if len(rates) > 1 else 0.0
+        return (f"{self.n_sample} macro cells of {self.wl} (seed 0, the same cells every step), literal n_b-corrector algorithm "
+                f"of hmm.py:334-369 with sparse LU, {len(rates)} timed pass(es), spread (max-min)/mean {spread:.1%}")
 
 
 # ---------------------------------------------------------------------------------------------
@@ -195,22 +164,22 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    budget = 20.0
-    rates = []
     t_all = time.perf_counter()
-    for s in range(args.warmup + args.steps):
-        r, cores, sample = cpu_reference_rate(args.workload, budget / max(1, args.steps + args.warmup))
-        if s >= args.warmup:
-            rates.append(r)
+    arm = CpuArm(args.workload)
+    for _ in range(min(args.warmup, 1)):  # one untimed pass warms caches and the page cache; more would only cost minutes
+        arm.step()
+    rates = [arm.step() for _ in range(args.steps)]
+    arm.close()
     value = float(np.mean(rates))
-    n_cells = int(np.prod(w["cells"])) * (2 if w["dim"] == 2 else 6) * world
+    n_cells = int(np.prod(W.macro_cells(args.workload, world, SHRINK, SCALING))) * (2 if w["dim"] == 2 else 6)
     line = {
         "impl": "reference", "metric": "micro cell solves/sec (FP64)", "value": value, "unit": "cell solves/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_cells / value * 1e3, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": n_cells / value * 1e3, "higher_is_better": True, "scaling": SCALING,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "macro_cells": n_cells,
-                   "note": "ms_per_step extrapolated from the bounded sample to the whole workload"},
-        "cpu_baseline": {"value": value, "unit": "cell solves/s", "cores": cores, "kind": "port", "sample": sample},
+                   "note": "each step = one pass over the fixed sample; ms_per_step extrapolated from the sample to the whole workload",
+                   "rates_per_step": rates},
+        "cpu_baseline": {"value": value, "unit": "cell solves/s", "cores": arm.procs, "kind": "port", "sample": arm.sample(rates)},
         "e2e": {"value": value, "unit": "cell solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
     }  # fmt: skip
@@ -245,7 +214,7 @@ def run_ours(args, rank, world, local_rank):
     sol.set_stream(stream.cuda_stream)
     n_local = d["hi"] - d["lo"]
     n_total = hmm._msh.num_cells
-    nnz = hmm._pattern.nnz
+    nnz, n_nodes = d["nnz"], d["n_nodes"]  # this rank's CSR slots and macro nodes (local numbering)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MiB > 126 MB L2
 
     def barrier():
@@ -259,7 +228,7 @@ def run_ours(args, rank, world, local_rank):
         """inputs already in HBM: cell kernel -> gather -> (halo sum)"""
         if ev:
             ev[0].record(stream)
-        sol.assemble_macro_dev(n_local, d["cells"], hmm._msh.num_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"])
+        sol.assemble_macro_dev(n_local, d["cells"], n_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"])
         if ev:
             ev[1].record(stream)
         sol.gather_csr_dev(nnz, d["ptr"], d["src"], d["S"], d["vals"])
@@ -303,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end: host buffers in, host buffers out ------------------------------------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
-    h_cells, h_xyz = pin(hmm._msh.cells[d["lo"] : d["hi"]].astype(np.int32)), pin(hmm._msh.x)
+    h_cells, h_xyz = pin(d["shard"].cells), pin(hmm._msh.x[d["shard"].nodes])
     h_ptr, h_src = pin(d["ptr"].cpu().numpy()), pin(d["src"].cpu().numpy())
     h_vals = torch.empty(nnz, dtype=torch.float64).pin_memory()
     h_it = torch.empty(n_local, dtype=torch.int32).pin_memory()
@@ -313,7 +282,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step_e2e():
         if world == 1:  # the host-buffer C-ABI entry point: copies in, kernels, copies out, sync
-            sol._check(sol.lib.hmx_assemble_macro(sol._h, n_local, h_cells.data_ptr(), hmm._msh.num_nodes, h_xyz.data_ptr(), nnz, h_ptr.data_ptr(),
+            sol._check(sol.lib.hmx_assemble_macro(sol._h, n_local, h_cells.data_ptr(), n_nodes, h_xyz.data_ptr(), nnz, h_ptr.data_ptr(),
                                        h_src.data_ptr(), h_vals.data_ptr(), None, h_it.data_ptr(), h_res.data_ptr()))  # fmt: skip
         else:  # sharded: the halo sum sits between the kernels and the copy-out
             d["cells"].copy_(h_cells, non_blocking=True)
@@ -321,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
             d["ptr"].copy_(h_ptr, non_blocking=True)
             d["src"].copy_(h_src, non_blocking=True)
             step_resident()
-            h_vals.copy_(d["vals"], non_blocking=True)
+            h_vals.copy_(d["vals"][:nnz], non_blocking=True)
             h_it.copy_(d["it"], non_blocking=True)
             h_res.copy_(d["res"], non_blocking=True)
             torch.cuda.synchronize()
@@ -338,7 +307,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = n_total * args.steps / e2e_s.item()
     if world == 1:  # the two paths agree bit for bit
-        assert np.array_equal(h_vals.numpy(), d["vals"].cpu().numpy())
+        assert np.array_equal(h_vals.numpy(), d["vals"][:nnz].cpu().numpy())
 
     # ---- roofline of the dominant kernel (the cell kernel), this rank ---------------------------
     flops = algorithmic_flops(w, n_local * args.steps, rhs_its) / args.steps
@@ -349,19 +318,25 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.workload)
 
-    # secondary workloads: parity-test configs and the axis-collapsed form, reported for context.
-    # At N > 1 only the collapsed headline config is repeated (every rank takes part).
+    # sharded == unsharded, proven inside the run: shared-row slots recomputed from ALL contributing cells on rank 0
+    halo_check = halo_self_check(hmm, local_rank) if world > 1 else None
+
+    # secondary workloads: parity-test configs, a coefficient that varies along all micro axes, the axis-collapsed
+    # form, and the STRONG-scaling wall times (the named mesh sizes of BASELINE configs[2..3] whatever N is).
+    # At N > 1 only the sharded entries are repeated (every rank takes part).
     other = {}
     if not args.no_extra:
         # cell_solver "auto": small hard elasticity cells (the collapsed C4 cell) are factorised directly (K5)
-        todo = ((("c2", False, "auto"), ("c3", False, "auto"), ("c4", True, "auto"), ("c4", True, "pcg"), ("c3", True, "auto"),
-                 ("c2", True, "auto")) if world == 1 else ((args.workload, True, "auto"),))  # fmt: skip
-        for name, collapse, how in todo:
-            if name == args.workload and not collapse:
+        todo = [("c4", False, "auto", "strong"), ("c3", False, "auto", "strong"), (args.workload, True, "auto", "weak")]
+        if world == 1:
+            todo += [("c2", False, "auto", "weak"), ("c3", False, "auto", "weak"), ("c4s", False, "auto", "weak"),
+                     ("c4", True, "pcg", "weak"), ("c3", True, "auto", "weak"), ("c2", True, "auto", "weak")]  # fmt: skip
+        for name, collapse, how, scaling in todo:
+            if name == args.workload and not collapse and scaling == SCALING:
                 continue
-            key = name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "")
+            key = name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "") + ("_strong" if scaling == "strong" else "")
             try:
-                other[key] = quick_rate(name, local_rank, collapse, world, how)
+                other[key] = quick_rate(name, local_rank, collapse, world, how, scaling)
             except Exception as e:  # never lose the headline line
                 other[key] = {"error": str(e)[:200]}
     if rank != 0:
@@ -371,11 +346,13 @@ def run_ours(args, rank, world, local_rank):
     # CPU baseline: bounded sample on the host cores
     cpu = None
     if not args.no_cpu and world == 1:  # rank 0 at N = 1 only (the other ranks' host cores idle otherwise)
-        r, cores, sample = cpu_reference_rate(args.workload, 15.0)
-        cpu = {"value": r, "unit": "cell solves/s", "cores": cores, "kind": "port", "sample": sample}
+        arm = CpuArm(args.workload)
+        rates = [arm.step()]
+        arm.close()
+        cpu = {"value": rates[0], "unit": "cell solves/s", "cores": arm.procs, "kind": "port", "sample": arm.sample(rates)}
     line = {
         "metric": "micro cell solves/sec (FP64)", "value": value, "unit": "cell solves/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "macro_cells": n_total, "macro_cells_per_gpu": n_local,
                    "macro_nnz": nnz, "axis_collapse": False, "cell_rtol": CELL_RTOL, "cell_atol": CELL_ATOL, "mean_pcg_iterations": mean_it,
@@ -387,28 +364,99 @@ def run_ours(args, rank, world, local_rank):
                      "unit": "TFLOP/s", "frac": flops / (cell_avg_ms * 1e-3) / 1e12 / fp64_peak, "traffic": traffic,
                      "peak_source": "FP64 DFMA microbenchmark of libhmx on this GPU (MEASURED_PEAKS.json has no FP64 entry)",
                      "cell_kernel_ms": cell_avg_ms, "cell_kernel_share_of_step": cell_avg_ms / float(np.mean(step_ms)),
-                     "algorithmic_flops_per_launch": flops, "copy_gbs_measured": copy_gbs},
-        "cpu_baseline": cpu, "other_workloads": other, "wall_s_timed_region": wall,
+                     "algorithmic_flops_per_launch": flops, "copy_gbs_measured": copy_gbs,
+                     "preconditioner": precond_note(w),
+                     "frac_incl_coarse_solve": (flops + coarse_flops(w, n_local, rhs_its / args.steps)) / (cell_avg_ms * 1e-3) / 1e12 / fp64_peak},
+        "cpu_baseline": cpu, "halo_check": halo_check, "other_workloads": other, "wall_s_timed_region": wall,
     }  # fmt: skip
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def quick_rate(name, device, collapse=False, world=1, cell_solver="auto"):
+def coarse_dofs(w):
+    """Unknowns of the coarse space of the two-level PCG for workload ``w`` (0 = block Jacobi)."""
+    from hommx_b200 import codegen, native
+    from hommx_b200 import ufl as pufl
+
+    name = next(k for k, v in WORKLOADS.items() if v is w)
+    A, Dt = W.coefficient(name, pufl)
+    return native.coarse_dofs(codegen.build_program(A, w["dim"], w["kind"], Dt), w["n"])
+
+
+def coarse_flops(w, n_pts, rhs_iterations):
+    """FLOPs of the dense coarse solves of the two-level preconditioner: one symmetric NCD x NCD matrix-vector product
+    per right-hand side and iteration, NCD^3 for the inversion per macro point (reported separately from the SURVEY 8d
+    count, which knows a Jacobi apply only)."""
+    ncd = coarse_dofs(w)
+    return rhs_iterations * 2.0 * ncd * ncd + n_pts * float(ncd) ** 3
+
+
+def precond_note(w):
+    ncd = coarse_dofs(w)
+    return ("block Jacobi" if ncd == 0 else
+            f"block Jacobi + additive coarse correction, {ncd} coarse unknowns inverted exactly per macro point (csrc/hmx_cell_coarse.cuh)")
+
+
+def halo_self_check(hmm, device, n_slots=256):
+    """Rank 0 recomputes a sample of the CSR slots it shares with other ranks from ALL contributing macro cells
+    (its own and its neighbours', solved again on this GPU) and compares with what the sharded assembly + halo sum
+    left in its value array: the parity proof of the multi-GPU path, inside the bench run itself."""
+    import torch
+
+    d = hmm._dev
+    sh = d["shard"]
+    if hmm._rank != 0:
+        return None
+    shared_local = sh.shared[sh.shared < sh.nnz]
+    if len(shared_local) == 0:
+        return {"slots": 0, "max_rel_diff": 0.0}
+    pick = shared_local[:: max(1, len(shared_local) // n_slots)][:n_slots]
+    gslots = sh.slots[pick]
+    sm = hmm._pattern.slot_map
+    cells = np.nonzero(np.isin(sm, gslots).any(axis=1))[0]
+    nodes, inv = np.unique(hmm._msh.cells[cells], return_inverse=True)
+    tdev = d["vals"].device
+    t_cells = torch.as_tensor(inv.reshape(len(cells), -1).astype(np.int32), device=tdev)
+    t_xyz = torch.as_tensor(np.ascontiguousarray(hmm._msh.x[nodes]), device=tdev)
+    nb2 = hmm._num_basis_functions_per_cell**2
+    S = torch.zeros((len(cells), nb2), dtype=torch.float64, device=tdev)
+    hmm._solver.assemble_macro_dev(len(cells), t_cells, len(nodes), t_xyz, 0, None, None, None, S, None, None)
+    hmm._solver.sync()
+    S = S.cpu().numpy()
+    want = np.zeros(len(gslots))
+    pos = {int(g): k for k, g in enumerate(gslots)}
+    for ci, c in enumerate(cells):
+        for e, g in enumerate(sm[c]):
+            k = pos.get(int(g))
+            if k is not None:
+                want[k] += S[ci, e]
+    got = d["vals"][torch.as_tensor(pick, device=tdev)].cpu().numpy()
+    scale = np.abs(want).max()
+    return {"slots": int(len(gslots)), "contributing_cells": int(len(cells)),
+            "cells_of_other_ranks": int(((cells < sh.lo) | (cells >= sh.hi)).sum()),
+            "max_rel_diff": float(np.abs(got - want).max() / scale)}
+
+
+def quick_rate(name, device, collapse=False, world=1, cell_solver="auto", scaling="weak"):
     import torch
     import torch.distributed as dist
 
-    hmm = build_solver(name, world, collapse=collapse, device=device, cell_solver=cell_solver)
+    global SCALING
+    saved, SCALING = SCALING, scaling
+    try:
+        hmm = build_solver(name, world, collapse=collapse, device=device, cell_solver=cell_solver)
+    finally:
+        SCALING = saved
     hmm._ensure_solver()
     sol, d = hmm._solver, hmm._dev
     sol.set_stream(torch.cuda.current_stream().cuda_stream)
     n = d["hi"] - d["lo"]
     best = 1e30
-    for _ in range(4):
+    for _ in range(3 if scaling == "strong" else 4):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        sol.assemble_macro_dev(n, d["cells"], hmm._msh.num_nodes, d["xyz"], hmm._pattern.nnz, d["ptr"], d["src"], d["vals"], d["S"],
+        sol.assemble_macro_dev(n, d["cells"], d["n_nodes"], d["xyz"], d["nnz"], d["ptr"], d["src"], d["vals"], d["S"],
                                d["it"], d["res"])  # fmt: skip
         if world > 1:
             hmm._halo_sum()
@@ -422,7 +470,8 @@ def quick_rate(name, device, collapse=False, world=1, cell_solver="auto"):
     n_all = hmm._msh.num_cells
     note = ("micro axes the coefficient does not depend on solved on one layer of cubes (exact symmetry reduction, "
             "same A_hom to 1e-10; DESIGN.md 4)") if collapse else "full n^d micro cell"
-    return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n_all, "n_gpus": world, "ms_per_step": best,
+    return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n_all, "n_gpus": world, "scaling": scaling,
+            "macro_assembly_wall_ms": best, "ms_per_step": best,
             "cell_solves_per_s": n_all / (best * 1e-3), "cell_solver": hmm.cell_solver_used,
             "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
 
@@ -437,9 +486,12 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--shrink", type=int, default=1, help="divide every macro mesh axis by this (ncu --set full captures)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one slab of macro cells per GPU (default); strong: the named mesh size of the config at every N")
     args = ap.parse_args()
-    global SHRINK
+    global SHRINK, SCALING
     SHRINK = max(1, args.shrink)
+    SCALING = args.scaling
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

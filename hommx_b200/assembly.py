@@ -87,3 +87,52 @@ def shared_slots(slot_map, n_cells, world, nnz):
         mark[slot_map[lo:hi].ravel()] = True
         touched += mark
     return np.nonzero(touched > 1)[0].astype(np.int64)
+
+
+@dataclass
+class LocalShard:
+    """Everything one rank keeps on its GPU, in LOCAL numbering: only the macro nodes its cells reference and only
+    the CSR value slots its cells touch (+ one dummy slot), so that the device state and the host<->device traffic
+    of a rank do not grow with the number of ranks (the reference keeps owned rows + ghosts per MPI rank the same
+    way).  ``slots`` maps local slot -> global CSR slot (sorted)."""
+
+    lo: int
+    hi: int
+    cells: np.ndarray  # (n_local, d+1) int32, local node ids
+    nodes: np.ndarray  # (n_local_nodes,) int64 global node id of every local node
+    slots: np.ndarray  # (nnz_local,) int64 global CSR slot of every local slot
+    gather: GatherMap  # over local slots
+    shared: np.ndarray  # (n_shared_global,) int64: local slot of every globally shared slot, nnz_local (dummy) if untouched
+    owned: np.ndarray  # (nnz_local,) bool: this rank contributes the slot to a globally complete value array
+
+    @property
+    def nnz(self):
+        return len(self.slots)
+
+
+def build_local_shard(cells, slot_map, nnz, rank, world):
+    """Local view of rank ``rank`` of ``world`` (contiguous cell blocks, ``shard_range``)."""
+    cells = np.asarray(cells)
+    n_cells = len(cells)
+    lo, hi = shard_range(n_cells, rank, world)
+    nodes, inv = np.unique(cells[lo:hi], return_inverse=True)
+    cells_l = inv.reshape(hi - lo, cells.shape[1]).astype(np.int32)
+    slots, sinv = np.unique(slot_map[lo:hi], return_inverse=True)
+    gm = build_gather(sinv.reshape(hi - lo, -1), len(slots))
+    owned = np.ones(len(slots), dtype=bool)
+    shared_local = np.zeros(0, dtype=np.int64)
+    if world > 1:
+        # lowest rank touching every slot (host, set-up only)
+        first = np.full(nnz, world, dtype=np.int32)
+        count = np.zeros(nnz, dtype=np.int32)
+        for r in range(world - 1, -1, -1):
+            rlo, rhi = shard_range(n_cells, r, world)
+            t = np.unique(slot_map[rlo:rhi])
+            first[t] = r
+            count[t] += 1
+        sh = np.nonzero(count > 1)[0].astype(np.int64)
+        pos = np.searchsorted(slots, sh)
+        hit = (pos < len(slots)) & (slots[np.minimum(pos, max(len(slots) - 1, 0))] == sh) if len(slots) else np.zeros(len(sh), bool)
+        shared_local = np.where(hit, pos, len(slots)).astype(np.int64)
+        owned = first[slots] == rank
+    return LocalShard(lo, hi, cells_l, nodes.astype(np.int64), slots.astype(np.int64), gm, shared_local, owned)

@@ -13,9 +13,12 @@
 //            of a Kuhn edge (1/2, 1/2), and the Galerkin matrix E1 = P1^T K P1 is the ordinary P1 stiffness matrix
 //            of the level-1 mesh with every coarse simplex carrying the MEAN of the coefficients (atoms) of the 2^D
 //            fine simplices it contains -- it is assembled directly, no operator applications are needed;
-//   level 2 (only when D * (NM/2)^D unknowns do not fit: NM = 8 in 3-D): one axis SA is coarsened once more by
-//            linear interpolation on the level-1 grid, E2 = P2^T E1 P2 (3-D, NM = 8: 2 x 4 x 4 nodes, 96 unknowns).
-//            SA is the first axis the coefficient does not depend on (CO::YDEP), axis 0 if it depends on all.
+//   level 2 (only when D * (NM/2)^D unknowns do not fit: NM = 8 in 3-D): along ONE axis SA the coefficient does not
+//            depend on (CO::YDEP) the level-1 functions are summed up, i.e. the coarse functions are constant along
+//            SA -- as the correctors are for such a coefficient -- E2 = P2^T E1 P2 (3-D, NM = 8: 1 x 4 x 4 nodes, 48
+//            unknowns).  A coefficient that depends on every axis gets no such step: semi-coarsening along an axis the
+//            coefficient varies on makes PCG SLOWER than block Jacobi (measured: 350 -> 570 iterations for a stiff
+//            ball at 8^3, scripts/study_preconditioners.py), so its 8^3 cell keeps block Jacobi.
 // E (+ a rank-D term gamma Z Z^T on the translations Z, so that the singular Galerkin matrix becomes definite
 // without changing the solution for the consistent residuals PCG produces) is inverted explicitly (symmetric
 // sweep operator, in place on the packed lower triangle); the apply is one dense symmetric matrix-vector product
@@ -53,7 +56,8 @@ HMX_HOSTDEV constexpr int kuhn_parent_type(int t, int b) {
   return -1;
 }
 
-template <class CO, int NM, int NT, int COLL, int VGLOB>
+// BASE: doubles of shared memory the kernel uses without the coarse space (the coarse arrays must fit on top).
+template <class CO, int NM, int NT, int COLL, int VGLOB, int BASE = 0>
 struct CoarseSpace {
   static constexpr int D = CO::DIM;
   static constexpr int T = kuhn_ntypes<D>();
@@ -62,16 +66,18 @@ struct CoarseSpace {
   static constexpr int NA1 = CO::NATOMS > 0 ? CO::NATOMS : 1;
   static constexpr int H = NM / 2;  // level-1 grid extent
   static constexpr int NC1 = ipow(H, D);
-  static constexpr int MAXDOF = 96;  // 96 x 97 / 2 doubles = 37 KB next to the vectors of an 8^3 cell
+  static constexpr int MAXDOF = 96;  // 96 x 97 / 2 doubles = 37 KB
+  static constexpr int SMEM_DOUBLES = 232448 / 8;  // 227 KB of dynamic shared memory per CTA
   static constexpr bool GEOM = HMX_PRECOND == 1 && COLL == 0 && VGLOB == 0 && NM % 2 == 0 && NM >= 4 && TPR >= 32;
-  static constexpr bool SEMI = GEOM && D * NC1 > MAXDOF && H % 2 == 0;
-  HMX_HOSTDEV static constexpr int semi_axis() {
+  // first axis the coefficient does not depend on, -1 if it depends on all
+  HMX_HOSTDEV static constexpr int invariant_axis() {
     for (int a = 0; a < D; ++a)
       if (!((CO::YDEP >> a) & 1)) return a;
-    return 0;
+    return -1;
   }
-  static constexpr int SA = semi_axis();
-  HMX_HOSTDEV static constexpr int m2(int a) { return a < D ? ((SEMI && a == SA) ? H / 2 : H) : 1; }
+  static constexpr bool SEMI = GEOM && D * NC1 > MAXDOF && invariant_axis() >= 0;
+  static constexpr int SA = invariant_axis() >= 0 ? invariant_axis() : 0;
+  HMX_HOSTDEV static constexpr int m2(int a) { return a < D ? ((SEMI && a == SA) ? 1 : H) : 1; }
   HMX_HOSTDEV static constexpr int stride1(int a) { return ipow(H, a); }  // level-1 node c sits in class-0 slot sum c_a H^a
   static constexpr int NC2 = m2(0) * m2(1) * m2(2);
   static constexpr int NCD = D * NC2;  // coarse unknowns, index = node * D + component
@@ -82,23 +88,26 @@ struct CoarseSpace {
   using CAI = AtomIdx<D, H, CO::YDEP, false>;  // level-1 cubes on the reduced (atom-dependent) axes, natural order
   static constexpr int NRC1 = CAI::NRC;
   static constexpr int setup_doubles = E1_DOUBLES + NA1 * T * NRC1;  // scratch of coarse_setup (the p / y area)
-  // on when the coarse unknowns fit, the set-up scratch fits in the p / y area and slots fit in 16 bits
-  static constexpr bool ON = GEOM && NCD <= MAXDOF && ipow(2, D) * NC1 <= 65535 && setup_doubles <= 2 * NRHS * D * ipow(2, D) * NC1;
   // shared scratch: set-up = scale vector + two column buffers + two pivots of the inversion (rows / columns padded
   // to the 16 x (NT / 16) thread grid); solve = the restricted residual of every right-hand side
   HMX_HOSTDEV static constexpr int inv_pad() {
     const int ra = (NCD + 15) / 16 * 16, rb = (NCD + NT / 16 - 1) / (NT / 16) * (NT / 16);
     return ra > rb ? ra : rb;
   }
-  static constexpr int CBUF = (3 * inv_pad() + 2 > NRHS * NCD ? 3 * inv_pad() + 2 : NRHS * NCD);
-  // level-1 class-0 slot of level-2 node C (natural index on the m2 grid)
+  static constexpr int CBUF = (3 * inv_pad() + 2 > NRHS * NCD ? 3 * inv_pad() + 2 : NRHS * NCD) + 2;
+  static constexpr int NPAR = (ipow(2, D) * NC1 + 1) / 2;  // parent table (16-bit pairs), in doubles
+  // on when the coarse unknowns fit, the set-up scratch fits in the p / y area, slots fit in 16 bits and the coarse
+  // arrays fit in shared memory on top of everything else
+  static constexpr bool ON = GEOM && NCD <= MAXDOF && ipow(2, D) * NC1 <= 65535 && setup_doubles <= 2 * NRHS * D * ipow(2, D) * NC1 &&
+                             BASE + NTRI + NPAR + CBUF <= SMEM_DOUBLES;
+  // level-1 class-0 slot of level-2 node C (natural index on the m2 grid; coordinate 0 along a summed-up axis)
   HMX_DEV static int slot2(int C) {
     int s = 0;
     HMX_UNROLL
     for (int a = 0; a < D; ++a) {
       const int ca = C % m2(a);
       C /= m2(a);
-      s += ca * ((SEMI && a == SA) ? 2 : 1) * stride1(a);
+      s += ca * stride1(a);
     }
     return s;
   }
@@ -126,10 +135,9 @@ HMX_DEV unsigned coarse_parents(int i) {
 
 // Galerkin coarse matrix of this macro point, inverted: s_ei <- (E + gamma Z Z^T)^-1, packed lower triangle.
 // Every thread of the CTA calls it; `work` (>= CS::setup_doubles doubles) is scratch, s_cbuf holds CS::NCD doubles.
-template <class CO, int NM, int NT, int COLL, int VGLOB>
+template <class CS, class CO, int NM, int NT>
 HMX_DEV void coarse_setup(const double* pc, const double (&Ms)[CO::DIM * CO::DIM], const double* s_atoms, double* work,
                           double* s_ei, double* s_cbuf, double* s_red, int red_stride, int& red_flip) {
-  using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB>;
   using AI = AtomIdx<CO::DIM, NM, CO::YDEP, true>;
   using CAI = typename CS::CAI;
   using G1 = Grid<CO::DIM, CS::H, 0>;
@@ -284,7 +292,7 @@ HMX_DEV void coarse_setup(const double* pc, const double (&Ms)[CO::DIM * CO::DIM
     }
     return sum;
   };
-  constexpr int NSUP = CS::SEMI ? 3 : 1;
+  constexpr int NSUP = CS::SEMI ? H : 1;  // level-1 nodes summed into one level-2 node (all H along SA), weight 1
   double diag[1] = {0.0};
   for (int e = t_id; e < NTRI; e += NT) {
     int i, j;
@@ -295,24 +303,20 @@ HMX_DEV void coarse_setup(const double* pc, const double (&Ms)[CO::DIM * CO::DIM
       int r = Ci, s = Cj;
       HMX_UNROLL
       for (int a = 0; a < D; ++a) {
-        ci[a] = (r % CS::m2(a)) * ((CS::SEMI && a == CS::SA) ? 2 : 1);
+        ci[a] = r % CS::m2(a);
         r /= CS::m2(a);
-        cj[a] = (s % CS::m2(a)) * ((CS::SEMI && a == CS::SA) ? 2 : 1);
+        cj[a] = s % CS::m2(a);
         s /= CS::m2(a);
       }
     }
     double sum = 0.0;
-    HMX_UNROLL
     for (int si = 0; si < NSUP; ++si) {
       int c[3] = {ci[0], ci[1], ci[2]};
-      const double wi = (NSUP == 1 || si == 1) ? 1.0 : 0.5;
-      if (NSUP > 1) c[CS::SA] = (ci[CS::SA] + si - 1 + H) % H;
-      HMX_UNROLL
+      if (NSUP > 1) c[CS::SA] = si;
       for (int sj = 0; sj < NSUP; ++sj) {
         int c2[3] = {cj[0], cj[1], cj[2]};
-        const double wj = (NSUP == 1 || sj == 1) ? 1.0 : 0.5;
-        if (NSUP > 1) c2[CS::SA] = (cj[CS::SA] + sj - 1 + H) % H;
-        sum += wi * wj * e1_entry(c, ki, c2, kj);
+        if (NSUP > 1) c2[CS::SA] = sj;
+        sum += e1_entry(c, ki, c2, kj);
       }
     }
     s_ei[e] = sum;
@@ -457,9 +461,8 @@ HMX_DEV double coarse_row_block(const double* s_ei, const double* s_r, int rb, i
 // s_r: NCD doubles of this right-hand side for the restricted residual.
 // OWN (thread l holds level-1 node l and its fine nodes 2 c + m): `splus` = r[2c] + 1/2 sum_m r[2c + m], summed by the
 // caller from its own registers, so that only the 2^D - 1 neighbours 2c - m are gathered here.
-template <class CO, int NM, int NT, int COLL, int VGLOB, int NP, bool PAIR, bool OWN>
-HMX_DEV void coarse_correct(double* y_q, const double* s_ei, double* s_r, int q, int l, const double (&splus)[CO::DIM]) {
-  using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB>;
+template <class CS, int NP, bool PAIR, bool OWN>
+HMX_DEV void coarse_correct(double* y_q, const double* s_ei, double* s_r, int q, int l, const double (&splus)[CS::D]) {
   constexpr int D = CS::D, H = CS::H, NC1 = CS::NC1, NC2 = CS::NC2, NCD = CS::NCD, TPR = CS::TPR, N = NP, HC = NC1;
   group_sync(1 + q, TPR);  // r of every node of this right-hand side is in y_q
   // level-1 restriction: r1[c] = r[2c] + 1/2 sum over the 2 (2^D - 1) Kuhn neighbours 2c +- m
@@ -522,13 +525,16 @@ HMX_DEV void coarse_correct(double* y_q, const double* s_ei, double* s_r, int q,
     }
   }
   group_sync(1 + q, TPR);
-  if (CS::SEMI) {
+  if (CS::SEMI) {  // level 2: sum over the level-1 nodes along SA
     for (int C = l; C < NC2; C += TPR) {
       const int s = CS::slot2(C);
-      const int cs = (s / CS::stride1(CS::SA)) % H;  // = 2 C_SA
-      const int sm = s + (((cs + H - 1) % H) - cs) * CS::stride1(CS::SA), sp = s + (((cs + 1) % H) - cs) * CS::stride1(CS::SA);
       HMX_UNROLL
-      for (int k = 0; k < D; ++k) s_r[C * D + k] = y_q[k * N + s] + 0.5 * (y_q[k * N + sm] + y_q[k * N + sp]);
+      for (int k = 0; k < D; ++k) {
+        double acc = y_q[k * N + s];
+        HMX_UNROLL
+        for (int t = 1; t < H; ++t) acc += y_q[k * N + s + t * CS::stride1(CS::SA)];
+        s_r[C * D + k] = acc;
+      }
     }
     group_sync(1 + q, TPR);
   }
@@ -545,13 +551,12 @@ HMX_DEV void coarse_correct(double* y_q, const double* s_ei, double* s_r, int q,
       }
   }
   group_sync(1 + q, TPR);
-  if (CS::SEMI) {  // level-1 nodes between two level-2 nodes along SA
+  if (CS::SEMI) {  // the coarse functions are constant along SA: copy to the other level-1 nodes of the line
     for (int c1 = l; c1 < NC1; c1 += TPR) {
       const int cs = (c1 / CS::stride1(CS::SA)) % H;
-      if (cs & 1) {
-        const int sm = c1 - CS::stride1(CS::SA), sp = c1 + (((cs + 1) % H) - cs) * CS::stride1(CS::SA);
+      if (cs != 0) {
         HMX_UNROLL
-        for (int k = 0; k < D; ++k) y_q[k * N + c1] = 0.5 * (y_q[k * N + sm] + y_q[k * N + sp]);
+        for (int k = 0; k < D; ++k) y_q[k * N + c1] = y_q[k * N + c1 - cs * CS::stride1(CS::SA)];
       }
     }
     group_sync(1 + q, TPR);

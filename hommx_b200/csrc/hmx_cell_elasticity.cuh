@@ -77,8 +77,8 @@ struct ElasticityLayout {
   // a plain store: y needs no zeroing between the sweeps
   static constexpr bool STORE1 = BLK && 32 % ((NM / 2) * (NM / 2)) == 0;
   // two-level preconditioner (hmx_cell_coarse.cuh): inverse coarse matrix, parent table, one column buffer
-  using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB>;
   static constexpr int o_ei = o_tab + (TAB ? N * 2 + (D == 3 ? (N + 1) / 2 : 0) : 0);  // [NTRI] packed lower triangle
+  using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB, o_ei>;
   static constexpr int o_par = o_ei + (CS::ON ? CS::NTRI : 0);                           // [NP] 2 x 16-bit level-1 slots
   static constexpr int o_cbuf = o_par + (CS::ON ? (NP + 1) / 2 : 0);                     // [CS::CBUF]
   static constexpr int total = o_cbuf + (CS::ON ? CS::CBUF : 0);
@@ -618,7 +618,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     }
     if constexpr (TWO) {
       // coarse Galerkin matrix of this point, inverted (uses the p / y area as scratch)
-      coarse_setup<CO, NM, NT, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_ei, s_cbuf, s_red, L::NSLOT * L::NREDV, red_flip);
+      coarse_setup<CS, CO, NM, NT>(pc, Ms, s_atoms, s_p, s_ei, s_cbuf, s_red, L::NSLOT * L::NREDV, red_flip);
       for (int i = t_id; i < NRHS * NDOF; i += NT) s_y[i] = 0.0;  // the accumulation target
     }
     sync();  // the preconditioner is complete before any group starts
@@ -700,7 +700,7 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
           }
         }
       }
-      coarse_correct<CO, NM, NT, COLL, VGLOB, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
+      coarse_correct<CS, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -765,6 +765,21 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         elasticity_sweep_blocks<CO, NM, NT, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
       else
         elasticity_sweep<CO, NM, NT, false, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
+      // (two-level) the old x and r come from the L2 scratch: issue those loads before the reduction of p.Kp, so
+      // that their latency runs under the reduction and its barrier instead of after it
+      constexpr int NPF = TWO ? NPT : 1;
+      double r_old[NPF][D], x_old[NPF][D];
+      if (TWO) {
+        HMX_UNROLL
+        for (int j = 0; j < NPF; ++j) {
+          const int i = l + j * TPR;
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) {
+            r_old[j][c] = i < N ? g_r[(q * D + c) * N + i] : 0.0;
+            x_old[j][c] = i < N ? g_x[(q * D + c) * N + i] : 0.0;
+          }
+        }
+      }
       double part = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
@@ -788,15 +803,15 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
             HMX_UNROLL
             for (int c = 0; c < D; ++c) {
               const int a = (q * D + c) * N + i;
-              const double rr = g_r[a] - alpha * s_y[a];
-              g_x[a] += alpha * s_p[a];
+              const double rr = r_old[j < NPF ? j : 0][c] - alpha * s_y[a];
+              g_x[a] = x_old[j < NPF ? j : 0][c] + alpha * s_p[a];
               g_r[a] = rr;
               s_y[a] = rr;
               if (OWN) splus[c] += j == 0 ? rr : 0.5 * rr;
             }
           }
         }
-        coarse_correct<CO, NM, NT, COLL, VGLOB, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
+        coarse_correct<CS, N, (L::o_cbuf % 2 == 0 && CS::NCD % 2 == 0), OWN>(s_y + (size_t)q * D * N, s_ei, s_cbuf + q * CS::NCD, q, l, splus);
         // z = M^-1 r overwrites r in y (the class-0 slots hold the coarse solution other threads still read: the z
         // of those nodes -- at most NKEEP per thread -- waits in registers)
         constexpr int NKEEP = (CS::NC1 + TPR - 1) / TPR;
@@ -922,6 +937,21 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
       }
       group_barrier();
     }
+    // the search directions are dead: their shared memory takes the correctors x, so that the cross products
+    // x_p . r_q below read every x_p from shared memory instead of the L2 scratch (the right-hand-side sweep does
+    // not read p)
+    constexpr bool XS = !VGLOB;
+    if (XS) {
+      HMX_UNROLL
+      for (int j = 0; j < NPT; ++j) {
+        const int i = l + j * TPR;
+        if (i < N) {
+          HMX_UNROLL
+          for (int c = 0; c < D; ++c) s_p[(q * D + c) * N + i] = g_x[(q * D + c) * N + i];
+        }
+      }
+    }
+    const double* x_all = XS ? s_p : g_x;
     elasticity_sweep<CO, NM, NT, true, COLL, VGLOB>(pc, Ms, s_atoms, s_p, s_y, q, l, sqrtw, s_tab);
     sync();  // x, r, b of every right-hand side are visible to the whole CTA
     {
@@ -934,11 +964,11 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         if (i < N) {
           HMX_UNROLL
           for (int c = 0; c < D; ++c) {
-            const double xq = g_x[(q * D + c) * N + i], rq = g_r[(q * D + c) * N + i];
+            const double xq = x_all[(q * D + c) * N + i], rq = g_r[(q * D + c) * N + i];
             HMX_UNROLL
             for (int p = 0; p < NRHS; ++p) {
-              z[p] += s_y[(p * D + c) * N + i] * xq;         // b_p . x_q
-              z[NRHS + p] += g_x[(p * D + c) * N + i] * rq;  // x_p . r_q
+              z[p] += s_y[(p * D + c) * N + i] * xq;          // b_p . x_q
+              z[NRHS + p] += x_all[(p * D + c) * N + i] * rq;  // x_p . r_q
             }
           }
         }

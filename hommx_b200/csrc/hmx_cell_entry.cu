@@ -5,14 +5,19 @@
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
 #ifndef HMX_VARIANT
-#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel, 1 = assembled operator (barrier-staged), 2 = assembled, TMA-staged, 3 = dense Cholesky
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel (PCG), 3 = dense Cholesky
 #endif
+// (variants 1 and 2 -- the assembled operator streamed from L2, barrier- or TMA-staged -- were measured slower than
+// variant 0 and live in experiments/assembled_operator/; they build only with -DHMX_EXPERIMENTAL_VARIANTS and that
+// directory on the include path)
 #if HMX_KIND == 0
 #include "hmx_cell_poisson.cuh"
 #else
 #include "hmx_cell_elasticity.cuh"
+#ifdef HMX_EXPERIMENTAL_VARIANTS
 #include "hmx_cell_elasticity_asm.cuh"
 #include "hmx_cell_elasticity_tma.cuh"
+#endif
 #include "hmx_cell_dense.cuh"
 #endif
 #include HMX_COEFF_FILE
@@ -30,14 +35,17 @@
 namespace {
 #if HMX_KIND == 0
 using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
-#elif HMX_VARIANT == 1
+#elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
-#elif HMX_VARIANT == 2
+#elif HMX_VARIANT == 2 && defined(HMX_EXPERIMENTAL_VARIANTS)
 using Layout = hmx::ElasticityTmaLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #elif HMX_VARIANT == 3
 using Layout = hmx::DenseLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
 #else
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
+#endif
+#ifndef HMX_EXPERIMENTAL_VARIANTS
+static_assert(HMX_KIND == 0 || HMX_VARIANT == 0 || HMX_VARIANT == 3, "elasticity kernel variants: 0 (matrix-free PCG) or 3 (dense Cholesky)");
 #endif
 static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled variant has no collapsed form");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
@@ -49,9 +57,9 @@ constexpr int kScratch = Layout::scratch_doubles;
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #if HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
-#elif HMX_VARIANT == 1
+#elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
-#elif HMX_VARIANT == 2
+#elif HMX_VARIANT == 2 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #elif HMX_VARIANT == 3
   hmx::elasticity_dense_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
@@ -68,9 +76,9 @@ static void emu_body(void* arg) {
   const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
 #if HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
-#elif HMX_VARIANT == 1
+#elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
-#elif HMX_VARIANT == 2
+#elif HMX_VARIANT == 2 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #elif HMX_VARIANT == 3
   hmx::elasticity_dense_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);

@@ -190,6 +190,22 @@ Driver& driver() {
   return d;
 }
 
+// Makes `device` current for the scope of one entry point and restores the caller's device afterwards (the library
+// must not change the calling thread's current device behind its back).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) status = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -308,6 +324,8 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
 
 extern "C" {
 
+int32_t hmx_abi_version(void) { return HMX_ABI_VERSION; }
+
 const char* hmx_last_error(const hmx_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int hmx_create(hmx_t** out, const hmx_desc* d) {
@@ -325,7 +343,8 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
     return fail(nullptr, HMX_ERR_CUDA, "no CUDA device available (the hot path has no CPU fallback)");
   }
   if (d->device < 0 || d->device >= ndev) return fail(nullptr, HMX_ERR_ARG, "device %d out of range (%d devices)", d->device, ndev);
-  HMX_CUDA(nullptr, cudaSetDevice(d->device));
+  DeviceGuard guard(d->device);
+  HMX_CUDA(nullptr, guard.status);
   HMX_CUDA(nullptr, cudaFree(nullptr));  // make the primary context current for the driver API
   Driver& drv = driver();
   if (!drv.ok) return fail(nullptr, HMX_ERR_CUDA, "%s", drv.why.c_str());
@@ -422,7 +441,7 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
 
 void hmx_destroy(hmx_t* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->work, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
                     &h->d_src, &h->d_vals, &h->d_S, &h->m_work})
@@ -472,7 +491,8 @@ int hmx_sync(hmx_t* h) {
 
 int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset) {
   if (!h || !total) return HMX_ERR_ARG;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   unsigned long long v = 0;
   HMX_CUDA(h, cudaMemcpyAsync(&v, h->work.p, sizeof v, cudaMemcpyDeviceToHost, h->stream));
   if (reset) HMX_CUDA(h, cudaMemsetAsync(h->work.p, 0, sizeof v, h->stream));
@@ -486,7 +506,8 @@ int hmx_gather_csr_dev(hmx_t* h, int64_t nnz, const int64_t* gather_ptr, const i
   if (!h) return HMX_ERR_ARG;
   if (nnz < 0 || (nnz > 0 && (!gather_ptr || !csr_vals))) return fail(h, HMX_ERR_ARG, "hmx_gather_csr: null CSR buffer");
   if (nnz == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   hmx_gather_csr<<<grid_1d(nnz, 256, h->info[6]), 256, 0, h->stream>>>(nnz, (const long long*)gather_ptr, gather_src, S_loc, csr_vals);
   HMX_CUDA(h, cudaGetLastError());
   return HMX_OK;
@@ -495,14 +516,16 @@ int hmx_gather_csr_dev(hmx_t* h, int64_t nnz, const int64_t* gather_ptr, const i
 int hmx_cell_tensors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, int32_t* iters, double* resid) {
   if (!h) return HMX_ERR_ARG;
   if (n_pts < 0 || (n_pts > 0 && (!x_pts || !A_hom))) return fail(h, HMX_ERR_ARG, "hmx_cell_tensors: null buffer");
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   return launch_cell(h, n_pts, x_pts, nullptr, nullptr, A_hom, nullptr, iters, resid);
 }
 
 int hmx_cell_correctors_dev(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom, double* chi) {
   if (!h) return HMX_ERR_ARG;
   if (n_pts < 0 || (n_pts > 0 && (!x_pts || !chi))) return fail(h, HMX_ERR_ARG, "hmx_cell_correctors: null buffer");
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   return launch_cell(h, n_pts, x_pts, nullptr, nullptr, A_hom, nullptr, nullptr, nullptr, chi);
 }
 
@@ -510,7 +533,8 @@ int hmx_cell_tensors(hmx_t* h, int64_t n_pts, const double* x_pts, double* A_hom
   if (!h) return HMX_ERR_ARG;
   if (n_pts < 0 || (n_pts > 0 && (!x_pts || !A_hom))) return fail(h, HMX_ERR_ARG, "hmx_cell_tensors: null buffer");
   if (n_pts == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   const size_t mm = (size_t)h->m() * h->m();
   HMX_CUDA(h, h->d_x.reserve(n_pts * 3 * sizeof(double)));
   HMX_CUDA(h, h->d_A.reserve(n_pts * mm * sizeof(double)));
@@ -538,7 +562,8 @@ int hmx_assemble_macro_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes,
   const size_t nb2 = (size_t)h->nb() * h->nb();
   if ((double)n_cells * (double)nb2 > 2147483647.0)
     return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: n_cells*n_b^2 exceeds the int32 range of gather_src; shard the cells");
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   double* S = S_loc;
   if (!S && n_cells > 0) {
     HMX_CUDA(h, h->d_S.reserve(n_cells * nb2 * sizeof(double)));
@@ -556,7 +581,8 @@ int hmx_assemble_macro(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, int
   if (n_cells < 0 || nnz < 0 || n_nodes < 0) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: negative size");
   if (n_cells > 0 && (!cell_nodes || !node_xyz)) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null mesh buffer");
   if (nnz > 0 && (!gather_ptr || !csr_vals)) return fail(h, HMX_ERR_ARG, "hmx_assemble_macro: null CSR buffer");
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   const int nv = h->dim + 1;
   const size_t nb2 = (size_t)h->nb() * h->nb();
   std::vector<int64_t> last(1, 0);
@@ -599,7 +625,8 @@ int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, in
   if (!h) return HMX_ERR_ARG;
   if (n < 0 || (n > 0 && (!csr_vals || !slots || !buf))) return fail(h, HMX_ERR_ARG, "hmx_halo_pack: null buffer");
   if (n == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   hmx_halo_pack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
   HMX_CUDA(h, cudaGetLastError());
   return HMX_OK;
@@ -609,7 +636,8 @@ int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_
   if (!h) return HMX_ERR_ARG;
   if (n < 0 || (n > 0 && (!csr_vals || !slots || !buf))) return fail(h, HMX_ERR_ARG, "hmx_halo_unpack: null buffer");
   if (n == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
   HMX_CUDA(h, cudaGetLastError());
   return HMX_OK;
@@ -621,7 +649,8 @@ int hmx_macro_lift_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const in
   if (n_dofs < 0 || (n_dofs > 0 && (!indptr || !indices || !csr_vals || !bc_mask || !bc_values || !b)))
     return fail(h, HMX_ERR_ARG, "hmx_macro_lift: null buffer");
   if (n_dofs == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   hmx_lift<<<grid_1d(n_dofs, 256, h->info[6]), 256, 0, h->stream>>>(n_dofs, (const long long*)indptr, indices, csr_vals,
                                                                      (const signed char*)bc_mask, bc_values, b);
   HMX_CUDA(h, cudaGetLastError());
@@ -636,7 +665,8 @@ int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int
   if (iters) *iters = 0;
   if (resid) *resid = 0.0;
   if (n_dofs == 0) return HMX_OK;
-  HMX_CUDA(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
   const long long n = n_dofs;
   HMX_CUDA(h, h->m_work.reserve((4 * (size_t)n + 8) * sizeof(double)));
   double* r = h->m_work.as<double>();
@@ -679,7 +709,8 @@ int hmx_measure_peaks(int32_t device, double* fp64_tflops, double* copy_gbs) {
     cudaGetLastError();
     return fail(nullptr, HMX_ERR_CUDA, "no CUDA device %d", device);
   }
-  HMX_CUDA(nullptr, cudaSetDevice(device));
+  DeviceGuard guard(device);
+  HMX_CUDA(nullptr, guard.status);
   cudaDeviceProp prop;
   HMX_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
   cudaEvent_t e0, e1;

@@ -16,7 +16,8 @@ function-space and Dirichlet objects are the light stand-ins of ``hommx_b200.mes
 ``hommx_b200.fem`` (a ``dolfinx.mesh.Mesh`` is accepted wherever its ``geometry`` /
 ``topology`` attributes suffice), coefficients are traced with ``hommx_b200.ufl`` (UFL's
 operator names), and the macro linear solve -- outside the hot path, PETSc KSP in the
-reference (hmm.py:482-483) -- is done with scipy.
+reference (hmm.py:482-483) -- is a Jacobi-PCG on the device (``hmx_macro_pcg_dev``) on the CSR values the
+assembly left there, or scipy's sparse LU on request (``{"pc_type": "lu"}``).
 """
 from __future__ import annotations
 
@@ -205,34 +206,45 @@ class BaseHMM:
         self._solver = mk(native.DENSE if self._cell_solver == "direct" else None)
         self.cell_solver_used = "direct" if self._solver.variant == native.DENSE else "pcg"
         tdev = torch.device("cuda", self._device)
-        n_cells = self._msh.num_cells
-        lo, hi = assembly.shard_range(n_cells, self._rank, self._world)
-        gm = assembly.build_gather(self._pattern.slot_map[lo:hi], self._pattern.nnz)
+        # device state in LOCAL numbering: the nodes this rank's cells reference, the CSR slots they touch (+ 1 dummy)
+        sh = assembly.build_local_shard(self._msh.cells, self._pattern.slot_map, self._pattern.nnz, self._rank, self._world)
+        lo, hi = sh.lo, sh.hi
         d = {
-            "lo": lo, "hi": hi,
-            "cells": torch.as_tensor(np.ascontiguousarray(self._msh.cells[lo:hi], dtype=np.int32), device=tdev),
-            "xyz": torch.as_tensor(self._msh.x, device=tdev),
-            "ptr": torch.as_tensor(gm.ptr, device=tdev),
-            "src": torch.as_tensor(gm.src, device=tdev),
-            "vals": torch.zeros(self._pattern.nnz, dtype=torch.float64, device=tdev),
+            "lo": lo, "hi": hi, "shard": sh, "n_nodes": len(sh.nodes), "nnz": sh.nnz,
+            "cells": torch.as_tensor(sh.cells, device=tdev),
+            "xyz": torch.as_tensor(np.ascontiguousarray(self._msh.x[sh.nodes]), device=tdev),
+            "ptr": torch.as_tensor(sh.gather.ptr, device=tdev),
+            "src": torch.as_tensor(sh.gather.src, device=tdev),
+            "vals": torch.zeros(sh.nnz + 1, dtype=torch.float64, device=tdev),  # last entry: dummy slot (stays 0)
             "S": torch.zeros((hi - lo, self._num_basis_functions_per_cell**2), dtype=torch.float64, device=tdev),
             "it": torch.zeros(hi - lo, dtype=torch.int32, device=tdev),
             "res": torch.zeros(hi - lo, dtype=torch.float64, device=tdev),
         }  # fmt: skip
         if self._world > 1:
-            sh = assembly.shared_slots(self._pattern.slot_map, n_cells, self._world, self._pattern.nnz)
-            d["shared"] = torch.as_tensor(sh, device=tdev)
-            d["halo"] = parallel.HaloExchange(d["shared"], torch.zeros(len(sh), dtype=torch.float64, device=tdev),
+            d["shared"] = torch.as_tensor(sh.shared, device=tdev)
+            d["halo"] = parallel.HaloExchange(d["shared"], torch.zeros(len(sh.shared), dtype=torch.float64, device=tdev),
                                               self._solver.halo_pack_dev, self._solver.halo_unpack_dev)
         self._dev = d
-        if self._cell_solver == "auto" and can_direct and self.cell_solver_used == "pcg" and hi > lo:
-            # K5 "only where it beats CG": PCG iterations on a sample of this rank's macro cells decide (deterministic;
-            # measured cross-over on B200: 15-40 iterations for 48-192 unknowns, scripts/probe_dense.py)
-            m = min(hi - lo, 256)
-            self._solver.rhs_iterations(reset=True)
-            self._solver.assemble_macro_dev(m, d["cells"], self._msh.num_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"])
-            self._solver.sync()
-            mean_it = self._solver.rhs_iterations(reset=True) / (m * self._solver.m)
+        if self._cell_solver == "auto" and can_direct and self.cell_solver_used == "pcg":
+            # K5 "only where it beats CG": PCG iterations on a sample of macro cells decide (measured cross-over on
+            # B200: 15-40 iterations for 48-192 unknowns, scripts/probe_dense.py).  The sample is spread over the
+            # rank's block and the mean is taken over ALL ranks (one all-reduce), so every rank runs the same kernel
+            # and a sharded assembly does not depend on how the cells were split.
+            idx = parallel.sample_cells(lo, hi)
+            m = len(idx)
+            its = 0
+            if m:
+                with torch.cuda.device(self._device):
+                    # the buffers below are torch allocations: the probe runs on torch's stream, after them
+                    self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+                    cells = d["cells"][torch.as_tensor(idx - lo, device=tdev)].contiguous()
+                    self._solver.rhs_iterations(reset=True)
+                    self._solver.assemble_macro_dev(m, cells, d["n_nodes"], d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"])
+                    self._solver.sync()
+                    its = self._solver.rhs_iterations(reset=True)
+            mean_it = its / max(m * self._solver.m, 1)
+            if self._world > 1:  # (an unsharded solver inside a multi-process job decides on its own)
+                mean_it = parallel.agree_on_mean(its, m * self._solver.m, device=tdev)
             if mean_it > DIRECT_ABOVE_ITERATIONS:
                 self._solver.close()
                 self._solver = mk(native.DENSE)
@@ -256,10 +268,10 @@ class BaseHMM:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
             self._solver.assemble_macro_dev(
-                d["hi"] - d["lo"], d["cells"], self._msh.num_nodes, d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"],
+                d["hi"] - d["lo"], d["cells"], d["n_nodes"], d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"],
             )  # fmt: skip
             ev[1].record()
-            self._solver.gather_csr_dev(self._pattern.nnz, d["ptr"], d["src"], d["S"], d["vals"])
+            self._solver.gather_csr_dev(d["nnz"], d["ptr"], d["src"], d["S"], d["vals"])
             ev[2].record()
             if self._world > 1:
                 self._halo_sum()
@@ -289,21 +301,32 @@ class BaseHMM:
         self._needs_reassembly = False
 
     def _halo_sum(self):
-        """Sum of the value slots shared between ranks: the only collective of the path."""
-        self._dev["halo"].sum(self._dev["vals"])
+        """Sum of the value slots shared between ranks: the only collective of the path.  The exchange buffer lists
+        every globally shared slot; a rank that does not touch one contributes its dummy slot (kept at zero)."""
+        vals = self._dev["vals"]
+        vals[-1:].zero_()
+        self._dev["halo"].sum(vals)
 
     def _full_values(self):
-        """Complete CSR values on every rank for the (host, scipy) macro solve; outside the hot path.
-        After the halo sum shared slots are complete everywhere and all other slots live on one rank."""
+        """Complete CSR values (global numbering) on every rank for the macro solve; outside the hot path.
+        After the halo sum shared slots are complete on every rank that touches them; each slot is contributed by
+        the lowest such rank."""
         import torch
         import torch.distributed as dist
 
         d = self._dev
+        sh = d["shard"]
+        local = d["vals"][: sh.nnz]
         if self._world == 1:
-            return d["vals"].cpu().numpy()
-        v = d["vals"].clone()
-        if self._rank != 0:
-            v[d["shared"]] = 0.0
+            v = torch.zeros(self._pattern.nnz, dtype=torch.float64, device=local.device)
+            v[torch.as_tensor(sh.slots, device=local.device)] = local
+            return v.cpu().numpy()
+        if "owned_slots" not in d:
+            own = np.nonzero(sh.owned)[0]
+            d["owned_local"] = torch.as_tensor(own, device=local.device)
+            d["owned_slots"] = torch.as_tensor(sh.slots[own], device=local.device)
+        v = torch.zeros(self._pattern.nnz, dtype=torch.float64, device=local.device)
+        v[d["owned_slots"]] = local[d["owned_local"]]
         dist.all_reduce(v, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         return v.cpu().numpy()
@@ -454,7 +477,7 @@ class PoissonPeriodicHMM:
     problem per direction gives the constant tensor ``A_hom`` (``compute_effective_tensor``,
     hmm.py:1219-1245) -- the one-point special case of the HMM cell kernel -- followed by a
     constant-coefficient macro problem (hmm.py:1247-1255).  No default boundary condition
-    (hmm.py:1132).  ``correctors`` are not returned by the cell kernel (gap)."""
+    (hmm.py:1132).  ``A_hom`` and ``correctors`` (hmm.py:1211-1217) come from ``hmx_cell_correctors_dev``."""
 
     def __init__(self, msh, A, f, msh_micro, eps, petsc_options_global_solve=None, petsc_options_cell_problem=None,
                  petsc_options_prefix="hommx_periodicHMM", *, quadrature_rule=None, device=None):  # fmt: skip

@@ -27,10 +27,11 @@ KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_coarse.cuh", "hmx_cell_elasticity.cuh",
-            "hmx_cell_elasticity_asm.cuh", "hmx_cell_elasticity_tma.cuh", "hmx_cell_dense.cuh", "hmx_cell_entry.cu")
-MATRIX_FREE, ASSEMBLED, ASSEMBLED_TMA, DENSE = 0, 1, 2, 3
+            "hmx_cell_dense.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, DENSE = 0, 3  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
+ABI_VERSION = 3  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -78,6 +79,7 @@ _lib_lock = threading.Lock()
 
 # name -> (restype, argtypes); every symbol include/hmx.h declares
 SYMBOLS = {
+    "hmx_abi_version": (C.c_int32, []),
     "hmx_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(hmx_desc)]),
     "hmx_destroy": (None, [C.c_void_p]),
     "hmx_last_error": (C.c_char_p, [C.c_void_p]),
@@ -106,13 +108,24 @@ SYMBOLS = {
 
 
 def load_library():
-    """dlopen hommx_b200/libhmx.so (building it first if the sources are newer)."""
+    """dlopen hommx_b200/libhmx.so.  With nvcc on the host the library is (re)built first whenever it is missing or
+    older than its sources; without nvcc the shipped binary is used.  Either way its ABI version must be the one
+    these bindings were written for: a stale library is refused instead of being called with the wrong arguments."""
     global _lib
     with _lib_lock:
         if _lib is None:
-            if not os.path.exists(LIB_PATH):
-                build_library()
+            have_nvcc = shutil.which("nvcc") is not None or os.path.exists("/usr/local/cuda/bin/nvcc")
+            if have_nvcc or not os.path.exists(LIB_PATH):
+                build_library()  # no-op when the library is newer than its sources
             lib = C.CDLL(LIB_PATH)
+            try:
+                lib.hmx_abi_version.restype = C.c_int32
+                got = int(lib.hmx_abi_version())
+            except AttributeError:
+                got = -1
+            if got != ABI_VERSION:
+                raise HmxError(f"{LIB_PATH} has ABI version {got}, these bindings need {ABI_VERSION}: rebuild it "
+                               "(python -c 'import __graft_entry__ as g; g.build()')")
             for name, (res, args) in SYMBOLS.items():
                 fn = getattr(lib, name)  # AttributeError if the symbol is not exported
                 fn.restype = res
@@ -124,34 +137,6 @@ def load_library():
 # ----------------------------------------------------------------------------
 # cell kernels
 # ----------------------------------------------------------------------------
-def assembled_fits(prog, n):
-    """The assembled elasticity variant needs one thread per node and p, r plus the two-stage ring in shared memory."""
-    if prog.kind == POISSON:
-        return False
-    d = prog.dim
-    N = n**d
-    nvec = d * d * (d + 1) // 2
-    nbq = (d * d + 1) // 2 * 2
-    ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
-    atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * n**ndep
-    smem = 8 * (2 * N * nvec + max(2 * nbq * N, atoms) + 2 * 32 * 12 + 64)
-    return N <= 1024 and smem <= SMEM_LIMIT
-
-
-def tma_fits(prog, n):
-    """The TMA-staged assembled variant: one thread per node with N a multiple of 32, p plus at least two ring
-    stages in shared memory."""
-    if prog.kind == POISSON:
-        return False
-    d = prog.dim
-    N = n**d
-    nvec = d * d * (d + 1) // 2
-    ndep = bin(prog.ydep & ((1 << d) - 1)).count("1")
-    atoms = max(1, prog.natoms) * (2 if d == 2 else 6) * n**ndep
-    fixed = 8 * (N * nvec + atoms + 2 * (N // 32) * 12 + 64)
-    return N % 32 == 0 and N <= 1024 and fixed + 2 * 8 * d * d * N <= SMEM_LIMIT
-
-
 def dense_dofs(prog, n, coll=0):
     d = prog.dim
     return d * n ** (d - bin(coll & ((1 << d) - 1)).count("1"))
@@ -163,24 +148,13 @@ def dense_fits(prog, n, coll=0):
 
 
 def default_variant(prog, n, collapse=False):
-    """Elasticity: the matrix-free element kernel; small cells (<= 192 unknowns, e.g. the axis-collapsed 8^3 cell
-    of BASELINE config 4) are factorised directly; the assembled (L2-streamed) variant is opt-in."""
+    """Elasticity: the matrix-free PCG kernel; ``HMX_ELASTICITY_VARIANT=dense`` forces the direct kernel where the
+    cell fits it (by default the drop-in classes decide from measured PCG iterations: hmm.py, cell_solver="auto")."""
     if prog.kind == POISSON:
         return MATRIX_FREE
-    forced = os.environ.get("HMX_ELASTICITY_VARIANT")
-    if forced == "matrix_free":
-        return MATRIX_FREE
-    if dense_fits(prog, n, collapse_mask(prog, collapse)) and (forced == "dense" or dense_default(prog, n, collapse)):
+    if os.environ.get("HMX_ELASTICITY_VARIANT") == "dense" and dense_fits(prog, n, collapse_mask(prog, collapse)):
         return DENSE
-    fits = assembled_fits(prog, n)
-    # measured on B200 (C4): the assembled variant reaches 33.4k cell solves/s against 36.4k of the
-    # matrix-free kernel (L2 latency is not hidden by 16 warps at 128 registers) -> opt-in only
-    return ASSEMBLED if (fits and os.environ.get("HMX_ELASTICITY_VARIANT") == "assembled") else MATRIX_FREE
-
-
-def dense_default(prog, n, collapse=False):
-    """Direct solve by default where it was measured faster than PCG (filled in from scripts/probe_dense.py)."""
-    return False
+    return MATRIX_FREE
 
 
 def collapse_mask(prog, collapse=True):
@@ -195,10 +169,6 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
     N = n ** (dim - bin(coll).count("1"))
     if kind != POISSON and variant == DENSE:
         return 256  # 16 x 16 owners of the register tile
-    if kind != POISSON and variant == ASSEMBLED:
-        return max(64, 32 * (-(-N // 32)))  # one thread per node
-    if kind != POISSON and variant == ASSEMBLED_TMA:
-        return N  # one thread per node (N % 32 == 0)
     if kind == POISSON:
         # four nodes per thread and several CTAs per SM beat two nodes per thread and one CTA
         # (measured on B200, scripts/probe_occ.py: C3 12.2M -> 19.0M, C2 7.0M -> 11.6M points/s)
@@ -276,6 +246,21 @@ def precond_mode(prog, variant=MATRIX_FREE):
     return 0 if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" else 1
 
 
+def coarse_dofs(prog, n, variant=MATRIX_FREE, coll=0):
+    """Unknowns of the coarse space the two-level PCG kernel builds for this coefficient and micro mesh (mirrors
+    ``CoarseSpace`` in csrc/hmx_cell_coarse.cuh, up to its shared-memory fit test); 0 = block Jacobi only."""
+    d = prog.dim
+    if not precond_mode(prog, variant) or coll or n % 2 or n < 4 or vectors_in_l2(prog, n, coll):
+        return 0
+    h = n // 2
+    nodes = h**d
+    if d * nodes > 96:  # the level-1 space does not fit: sum it up along an axis the coefficient does not depend on
+        if prog.ydep == (1 << d) - 1:
+            return 0
+        nodes //= h
+    return d * nodes if d * nodes <= 96 else 0
+
+
 def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE, coll=0):
     kind = "p" if prog.kind == POISSON else "e"
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
@@ -309,19 +294,31 @@ def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_
     cubin = os.path.join(KCACHE, key + ".cubin")
     if os.path.exists(cubin) and not force:
         return cubin
+    # every rank of a torchrun launch may compile the same key at once on a cold cache: each process writes its own
+    # temporary files (coefficient header, cubin, log) and renames them into place, so nobody reads a half-written one
+    uniq = f".tmp{os.getpid()}_{threading.get_ident()}"
     coeff = os.path.join(KCACHE, key + ".coeff.cuh")
-    with open(coeff, "w") as f:
+    coeff_tmp = os.path.join(KCACHE, key + uniq + ".coeff.cuh")
+    with open(coeff_tmp, "w") as f:
         f.write(prog.source)
-    tmp = cubin + f".tmp{os.getpid()}"
+    tmp = cubin + uniq
     cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", "-Xptxas", "-v", "-I", CSRC,
-           *kernel_defines(prog, n, threads, coeff, min_blocks, variant, coll), *_extra_flags(), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
-    if keep_log:
-        with open(os.path.join(KCACHE, key + ".ptxas.log"), "w") as f:
-            f.write(" ".join(cmd) + "\n" + r.stderr)
-    os.replace(tmp, cubin)
+           *kernel_defines(prog, n, threads, coeff_tmp, min_blocks, variant, coll), *_extra_flags(), "-o", tmp, os.path.join(CSRC, "hmx_cell_entry.cu")]  # fmt: skip
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise HmxError(f"nvcc failed for cell kernel {key}:\n{r.stderr[-4000:]}")
+        if keep_log:
+            log_tmp = os.path.join(KCACHE, key + uniq + ".ptxas.log")
+            with open(log_tmp, "w") as f:
+                f.write(" ".join(cmd).replace(coeff_tmp, coeff) + "\n" + r.stderr)
+            os.replace(log_tmp, os.path.join(KCACHE, key + ".ptxas.log"))
+        os.replace(coeff_tmp, coeff)
+        os.replace(tmp, cubin)
+    finally:
+        for leftover in (coeff_tmp, tmp):
+            if os.path.exists(leftover):
+                os.remove(leftover)
     return cubin
 
 
@@ -339,6 +336,7 @@ class CellSolver:
     def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None,
                  min_blocks=None, variant=None, collapse=False):
         self.prog = prog
+        self.device = int(device)
         self.dim, self.kind, self.n = prog.dim, prog.kind, int(n_micro)
         self.m = prog.n_rhs
         self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
@@ -448,14 +446,17 @@ class CellSolver:
         n, d = len(x), self.dim
         bs = 1 if self.kind == POISSON else d
         shape = [1 if (self.collapse_mask >> a) & 1 else self.n for a in range(d)]
-        dev = torch.device("cuda", torch.cuda.current_device())
-        xd = torch.as_tensor(x, device=dev)
-        A = torch.empty((n, self.m, self.m), dtype=torch.float64, device=dev)
-        chi = torch.zeros((n, self.m, bs) + tuple(reversed(shape)), dtype=torch.float64, device=dev)
-        self._check(self.lib.hmx_cell_correctors_dev(self._h, n, self._dp(xd), self._dp(A), self._dp(chi)))
-        self.sync()
-        full = (n, self.m, bs) + (self.n,) * d
-        return A.cpu().numpy(), np.broadcast_to(chi.cpu().numpy(), full).copy()
+        dev = torch.device("cuda", self.device)  # the handle's device, whatever the caller's current device is
+        with torch.cuda.device(dev):
+            # the zero-fill and the uploads are torch work: the kernel must run on the same stream (or after them)
+            self.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+            xd = torch.as_tensor(x, device=dev)
+            A = torch.empty((n, self.m, self.m), dtype=torch.float64, device=dev)
+            chi = torch.zeros((n, self.m, bs) + tuple(reversed(shape)), dtype=torch.float64, device=dev)
+            self._check(self.lib.hmx_cell_correctors_dev(self._h, n, self._dp(xd), self._dp(A), self._dp(chi)))
+            self.sync()
+            full = (n, self.m, bs) + (self.n,) * d
+            return A.cpu().numpy(), np.broadcast_to(chi.cpu().numpy(), full).copy()
 
     def assemble_macro_dev(self, n_cells, cell_nodes, n_nodes, node_xyz, nnz, gather_ptr, gather_src, csr_vals, S_loc=None,
                            iters=None, resid=None):

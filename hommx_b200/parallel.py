@@ -34,3 +34,30 @@ class HaloExchange:
     @property
     def bytes_per_exchange(self):
         return self.n * 8
+
+
+def sample_cells(lo, hi, max_samples=256):
+    """Indices of at most ``max_samples`` macro cells spread evenly over the rank's block ``[lo, hi)`` (a contiguous
+    first block would not be representative of an x-dependent coefficient)."""
+    import numpy as np
+
+    n = hi - lo
+    if n <= 0:
+        return np.zeros(0, dtype=np.int64)
+    m = min(n, max_samples)
+    return lo + (np.arange(m, dtype=np.int64) * n) // m
+
+
+def agree_on_mean(local_sum, local_count, device=None, group=None):
+    """Mean of a per-rank statistic over ALL ranks (one all-reduce of two numbers), so that a decision derived from
+    it -- which cell kernel to run -- is the same on every rank: the sharded assembly then equals the single-GPU one
+    bit for bit wherever the summation order allows.  Without an initialised process group: the local mean."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local_sum / max(local_count, 1)
+    t = torch.tensor([float(local_sum), float(local_count)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    s, c = t.tolist()
+    return s / max(c, 1.0)

@@ -28,6 +28,12 @@ extern "C" {
 
 typedef struct hmx_handle hmx_t;
 
+/* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
+ * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
+ * to new Python sources would otherwise be called with the wrong arguments). */
+#define HMX_ABI_VERSION 3
+int32_t hmx_abi_version(void);
+
 enum hmx_status {
   HMX_OK = 0,
   HMX_ERR_ARG = -1,     /* invalid argument (the reference raises ValueError, hmm.py:104-115) */

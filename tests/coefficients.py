@@ -8,14 +8,19 @@ each docstring, relative to /root/reference).
 """
 import math
 
+# the BASELINE workloads' coefficients live in the package (bench.py and examples/ use them too): one source text
+from hommx_b200.workloads import (  # noqa: F401
+    circle_indicator as _circle,
+    dtheta_rotation_3d,
+    dtheta_wavy,
+    hooke,
+    hooke_fibre_3d,
+    hooke_spheres_3d,
+    laminate,
+    smooth_sin,
+)
 
-def smooth_sin(ufl):
-    """examples/hmm.py:15-16, examples/hmm_3d.py:14-15, test_integration_poisson.py:244-245,484-485"""
 
-    def A(x, y):
-        return 1.1 + x[0] + ufl.sin(2 * ufl.pi * y[0])
-
-    return A
 
 
 def analytic1(ufl):
@@ -54,20 +59,8 @@ def x_only(ufl):
     return A
 
 
-def laminate(ufl):
-    """examples/diffusion/laminate.py:101-102"""
-
-    def A(x, y):
-        return ufl.conditional(ufl.cos(2 * ufl.pi * y[0]) < 0, 5, 0.05)
-
-    return A
 
 
-def _circle(ufl, a, b, r=0.25):
-    """examples/diffusion/inclusion.py:107-114, examples/linear_elasticity/rotated_fibers.py:23-29"""
-    dx = ufl.acos(ufl.cos(2 * ufl.pi * (a - 1 / 2)))
-    dy = ufl.acos(ufl.cos(2 * ufl.pi * (b - 1 / 2)))
-    return (dx**2 + dy**2) < ((2 * ufl.pi) ** 2 * r**2)
 
 
 def inclusion(ufl):
@@ -119,14 +112,6 @@ def dtheta_test_stratified(ufl, theta_factor=0.2):
     return Dtheta
 
 
-def dtheta_wavy(ufl):
-    """examples/diffusion/laminate.py:109-117 completed to a square matrix:
-    theta(x) = (x1 - sin 2 pi x0, x0)."""
-
-    def Dtheta(x):
-        return ufl.as_matrix([[-2 * ufl.pi * ufl.cos(2 * ufl.pi * x[0]), 1.0], [1.0, 0.0]])
-
-    return Dtheta
 
 
 def dtheta_inclusion(ufl):
@@ -139,18 +124,6 @@ def dtheta_inclusion(ufl):
     return Dtheta
 
 
-def dtheta_rotation_3d(ufl, W=0.4):
-    """examples/linear_elasticity/rotated_fibers.py:41-63 completed to a square rotation about
-    the x1 axis by gamma(x1) = pi x1 / (2 W)."""
-
-    def Dtheta(x):
-        g = 1 / 2 * ufl.pi * x[1] / W
-        R = ufl.as_matrix(
-            [[ufl.cos(g), 0.0, -ufl.sin(g)], [0.0, 1.0, 0.0], [ufl.sin(g), 0.0, ufl.cos(g)]]
-        )
-        return ufl.transpose(R)
-
-    return Dtheta
 
 
 def dtheta_shear_3d(ufl):
@@ -163,19 +136,6 @@ def dtheta_shear_3d(ufl):
 
 
 # ---- elasticity ----
-def hooke(ufl, dim, mu, lambda_):
-    """test/integration/test_integration_linear_elasticity.py:84-94,234-244;
-    examples/linear_elasticity/rotated_fibers.py:66-76"""
-
-    def A(x, y):
-        I = ufl.Identity(dim)
-        i, j, k, l = ufl.indices(4)
-        return ufl.as_tensor(
-            lambda_(x, y) * I[i, j] * I[k, l] + mu(x, y) * (I[i, k] * I[j, l] + I[i, l] * I[j, k]),
-            indices=(i, j, k, l),
-        )
-
-    return A
 
 
 def hooke_sin_2d(ufl):
@@ -188,11 +148,6 @@ def hooke_const_3d(ufl):
     return hooke(ufl, 3, lambda x, y: 1, lambda x, y: 1.25)
 
 
-def hooke_fibre_3d(ufl, mu_in=100, mu_out=0.001):
-    """examples/linear_elasticity/rotated_fibers.py:23-38"""
-    return hooke(
-        ufl, 3, lambda x, y: ufl.conditional(_circle(ufl, y[1], y[2]), mu_in, mu_out), lambda x, y: 1
-    )
 
 
 def hooke_smooth_3d(ufl):

@@ -87,24 +87,6 @@ def test_dense_cholesky_variant_matches_oracle(case, collapse):
     ref.close()
 
 
-ELAST = [c for c in ALL if c.kind == 1 and native.assembled_fits(K.program(c), c.n)]
-
-
-@pytest.mark.parametrize("case", ELAST, ids=[c.name for c in ELAST])
-def test_assembled_elasticity_variant_matches_oracle(case):
-    """The opt-in variant that assembles the micro operator into an L2-resident buffer."""
-    prog = K.program(case)
-    qp, qw = K.tables(case, prog)
-    s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=native.ASSEMBLED)
-    x = K.points(case, 3)
-    Ah = s.cell_tensors(x)
-    mic = K.oracle_cell(case, prog)
-    for k in range(len(x)):
-        Ao = K.oracle_tensor(case, mic, x[k])
-        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
-    s.close()
-
-
 COLLAPSIBLE = [c for c in ALL if K.program(c).ydep != (1 << c.dim) - 1]
 
 
@@ -116,25 +98,6 @@ def test_axis_collapse_is_exact(case):
     qp, qw = K.tables(case, prog)
     s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, collapse=True)
     x = K.points(case, 3)
-    Ah = s.cell_tensors(x)
-    mic = K.oracle_cell(case, prog)
-    for k in range(len(x)):
-        Ao = K.oracle_tensor(case, mic, x[k])
-        assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
-    s.close()
-
-
-ELAST_TMA = [c for c in ALL if c.kind == 1 and native.tma_fits(K.program(c), c.n)]
-
-
-@pytest.mark.parametrize("case", ELAST_TMA, ids=[c.name for c in ELAST_TMA])
-def test_tma_staged_elasticity_variant_matches_oracle(case):
-    """Opt-in variant: assembled operator streamed through a cp.async.bulk / mbarrier ring."""
-    prog = K.program(case)
-    qp, qw = K.tables(case, prog)
-    s = native.CellSolver(prog, case.n, qp, qw, rtol=case.rtol, variant=native.ASSEMBLED_TMA)
-    s.set_grid(3)  # several macro points per CTA: barriers are re-initialised between points
-    x = K.points(case, 8)
     Ah = s.cell_tensors(x)
     mic = K.oracle_cell(case, prog)
     for k in range(len(x)):
@@ -240,4 +203,42 @@ def test_nvrtc_built_kernel_matches_oracle(monkeypatch):
     for k in range(len(x)):
         Ao = K.oracle_tensor(case, mic, x[k])
         assert np.abs(Ah[k] - Ao).max() <= case.tol * np.abs(Ao).max()
+    s.close()
+
+
+@pytest.mark.parametrize("precond", ["twolevel", "jacobi"])
+def test_c4_full_cell_local_matrices_at_32_macro_cells(precond, monkeypatch):
+    """The bench headline kernel (BASELINE config 4: full 8^3 fibre cell, 6 right-hand sides) against the oracle at
+    32 random macro cells of the beam [0,1] x [0,0.4] x [0,0.1]: the 12 x 12 local matrices S_loc (not only A_hom)
+    against the tensor form of the oracle at every cell and against the LITERAL restatement of hmm.py:334-369
+    (n_b = 12 eps-scaled correctors, 144 integrals) at 6 of them; both preconditioners of the PCG kernel."""
+    monkeypatch.setenv("HMX_PRECOND", precond)
+    case = K.BY_NAME["e3_fibre_rot_n8_c4"]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-9, atol=1e-12)
+    rng = np.random.default_rng(32)
+    n = 32
+    base = rng.uniform([0.05, 0.02, 0.005], [0.9, 0.36, 0.09], (n, 3))
+    ref = np.zeros((4, 3))
+    ref[1:] = np.eye(3) * np.array([0.05, 0.02, 0.008])
+    xyz = (base[:, None, :] + ref[None] + rng.uniform(-0.002, 0.002, (n, 4, 3))).reshape(-1, 3)
+    cells = np.arange(4 * n, dtype=np.int32).reshape(n, 4)
+    nb2 = s.nb * s.nb
+    gp = np.arange(n * nb2 + 1, dtype=np.int64)
+    gs = np.arange(n * nb2, dtype=np.int32)
+    _, S, it, res = s.assemble_macro(cells, xyz, gp, gs, want_local=True, return_stats=True)
+    mic = K.oracle_cell(case)
+    A = getattr(K.Cf, case.coeff)(K.npufl)
+    Dn = getattr(K.Cf, case.dtheta)(K.npufl)
+    Dt = lambda x: np.asarray(Dn(np.asarray(x, float)))[..., 0]  # noqa: E731
+    for k in range(n):
+        verts = xyz[cells[k]]
+        So = ho.local_stiffness_from_tensor(K.oracle_tensor(case, mic, verts.mean(axis=0)), verts, mic.kind)
+        assert np.abs(S[k] - So).max() <= 1e-10 * np.abs(So).max(), (k, it[k], res[k])
+        if k % 6 == 0:
+            Sl = ho.local_stiffness_literal(mic, A, verts, 0.01, Dt)
+            assert np.abs(S[k] - Sl).max() <= 1e-10 * np.abs(Sl).max(), (k, "literal")
+    if precond == "twolevel":
+        assert it.max() < 200  # block Jacobi needs ~250 on this cell
     s.close()

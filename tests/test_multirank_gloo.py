@@ -62,3 +62,32 @@ def test_sharded_assembly_with_halo_exchange(world, bs):
     out = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), bs, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world)), dict(out)
+
+
+def _decision_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # rank 0 sees an easy coefficient region (10 iterations per solve), rank 1 a hard one (200), rank 2 has no cells:
+    # decided alone they would pick different cell kernels; the collective mean is the same number everywhere
+    n_solves = [256 * 6, 128 * 6, 0][rank]
+    its = [10, 200, 0][rank] * n_solves
+    out[rank] = parallel.agree_on_mean(its, n_solves)
+    dist.destroy_process_group()
+
+
+def test_cell_solver_decision_is_collective():
+    """cell_solver="auto" (hommx_b200/hmm.py): the PCG-vs-direct decision is taken from the iteration mean over the
+    samples of ALL ranks, so that every rank runs the same kernel."""
+    world = 3
+    out = mp.Manager().dict()
+    mp.spawn(_decision_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    want = (10 * 256 * 6 + 200 * 128 * 6) / (256 * 6 + 128 * 6)
+    assert all(abs(out[r] - want) < 1e-12 for r in range(world)), dict(out)
+    assert parallel.agree_on_mean(30.0, 3) == 10.0  # no process group: the local mean
+
+
+def test_sample_cells_spreads_over_the_block():
+    idx = parallel.sample_cells(1000, 1000 + 5000, 256)
+    assert len(idx) == 256 and idx[0] == 1000 and idx[-1] >= 1000 + 5000 - 5000 // 256 - 1 and np.all(np.diff(idx) > 0)
+    assert list(parallel.sample_cells(7, 10)) == [7, 8, 9] and len(parallel.sample_cells(5, 5)) == 0
