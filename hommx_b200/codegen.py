@@ -85,9 +85,7 @@ def _numeric_equal(a: Expr, b: Expr, dim, rng):
 
 
 def _trace_components(A, dim, kind):
-    x = ufl.Coordinate("x", 3)
-    y = ufl.Coordinate("y", dim)
-    val = A(x, y)
+    val = ufl.call_traced(A, [("const", "x"), ("coord", "y", dim)])  # hmm.py:198: A(x_macro, y)
     rng = np.random.default_rng(0)
     if kind == POISSON:
         if isinstance(val, Tensor):
@@ -125,8 +123,7 @@ def _trace_components(A, dim, kind):
 
 
 def _trace_dtheta(Dtheta_transpose, dim):
-    x = ufl.Coordinate("x", 3)
-    M = Dtheta_transpose(x)
+    M = ufl.call_traced(Dtheta_transpose, [("const", "x")])  # hmm.py:757: Dtheta_transpose(x_macro)
     if not isinstance(M, Tensor) or M.data.shape != (dim, dim):
         shape = getattr(getattr(M, "data", None), "shape", None)
         raise ValueError(
@@ -468,3 +465,54 @@ struct HMX_COEFF {{
         dim=dim, kind=kind, stratified=dth is not None, degree=degree, ydep=ydep, natoms=natoms, npc=npc,
         ncomp=len(comps), scalar=scalar, source=src, atoms=atoms, comps=comps, dtheta=dth,
     )  # fmt: skip
+
+
+# ----------------------------------------------------------------------------
+# macro right-hand side f(x)  (hmm.py:131-133: L = inner(f(x), v) dx)
+# ----------------------------------------------------------------------------
+@dataclass
+class LoadProgram:
+    dim: int
+    bs: int
+    degree: int  # quadrature degree of inner(f, v) dx: degree(f) + 1 for the P1 test function
+    source: str
+
+    @property
+    def key(self):
+        return hashlib.sha1(self.source.encode()).hexdigest()[:16]
+
+
+def trace_load(f, dim, bs):
+    """Components of the macro right-hand side ``f(x)`` (a scalar for the Poisson classes, a ``bs``-vector for
+    elasticity) as traced expressions of the macro coordinate."""
+    val = ufl.call_traced(f, [("coord", "x", dim)])  # hmm.py:131: f(SpatialCoordinate(msh))
+    if isinstance(val, Tensor):
+        comps = [val.data[k] for k in range(val.data.shape[0])]
+    elif isinstance(val, (list, tuple, np.ndarray)):
+        comps = [Expr.wrap(v) for v in val]
+    else:
+        comps = [Expr.wrap(val)]
+    if len(comps) != bs:
+        raise ValueError(f"f must have {bs} component(s), got {len(comps)}")
+    return comps
+
+
+def build_load_program(f, dim, bs) -> LoadProgram:
+    """CUDA source of ``struct HMX_LOAD`` for csrc/hmx_load_entry.cu: the device-side replacement of the FFCx kernel
+    the reference assembles ``self._L`` with (hmm.py:445-450)."""
+    comps = trace_load(f, dim, bs)
+    degree = max(ufl.estimate_degree(c, {"x": 1}) for c in comps) + 1
+    em = _Emitter({("x", k): f"x[{k}]" for k in range(3)}, "f")
+    body = _body(em.lines, [em.ref(c) for c in comps], "out")
+    src = f"""// hommx_b200 load program v1
+struct HMX_LOAD {{
+  static constexpr int DIM = {dim};
+  static constexpr int BS = {bs};
+  static constexpr int QDEG = {degree};
+  __device__ __forceinline__ static void eval(const double* __restrict__ x, double* __restrict__ out) {{
+    (void)x; (void)out;
+{body}
+  }}
+}};
+"""
+    return LoadProgram(dim, bs, degree, src)

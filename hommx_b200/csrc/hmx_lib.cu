@@ -243,6 +243,12 @@ struct hmx_handle {
   // staging for the host-pointer entry points
   DevBuf d_x, d_A, d_it, d_res, d_cells, d_xyz, d_ptr, d_src, d_vals, d_S;
   DevBuf m_work;  // macro PCG: r, p, y, dinv, scalars
+  // macro load vector (hmx_macro_load_dev): the module of the last f, its quadrature table
+  CUmodule load_module = nullptr;
+  CUfunction load_fn = nullptr;
+  unsigned long long load_hash = 0;
+  int load_info[4] = {0, 0, 0, 0};
+  DevBuf l_qp, l_qw;
   mutable std::string err;
   int ntypes() const { return dim == 2 ? 2 : 6; }
   int m() const { return kind == HMX_POISSON ? dim : dim * (dim + 1) / 2; }
@@ -444,8 +450,9 @@ void hmx_destroy(hmx_t* h) {
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->work, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
-                    &h->d_src, &h->d_vals, &h->d_S, &h->m_work})
+                    &h->d_src, &h->d_vals, &h->d_S, &h->m_work, &h->l_qp, &h->l_qw})
     b->release();
+  if (h->load_module && driver().ok) driver().ModuleUnload(h->load_module);
   if (h->module && driver().ok) driver().ModuleUnload(h->module);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -640,6 +647,54 @@ int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_
   HMX_CUDA(h, guard.status);
   hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
   HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+int hmx_macro_load_dev(hmx_t* h, const void* image, size_t image_size, int64_t n_cells, const int32_t* cell_nodes,
+                       const double* node_xyz, int32_t nq, const double* qp, const double* qw, double* Fe) {
+  if (!h) return HMX_ERR_ARG;
+  if (!image || image_size == 0) return fail(h, HMX_ERR_KERNEL, "hmx_macro_load: no kernel image (the CUDA path has no fallback)");
+  if (n_cells < 0 || nq < 1 || !qp || !qw || (n_cells > 0 && (!cell_nodes || !node_xyz || !Fe)))
+    return fail(h, HMX_ERR_ARG, "hmx_macro_load: null buffer or empty quadrature rule");
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
+  Driver& drv = driver();
+  unsigned long long hash = 1469598103934665603ULL;  // FNV-1a of the image: a new f loads a new module
+  for (size_t i = 0; i < image_size; ++i) hash = (hash ^ static_cast<const unsigned char*>(image)[i]) * 1099511628211ULL;
+  if (!h->load_fn || hash != h->load_hash) {
+    if (h->load_module) {
+      HMX_CUDA(h, cudaStreamSynchronize(h->stream));
+      drv.ModuleUnload(h->load_module);
+      h->load_module = nullptr;
+      h->load_fn = nullptr;
+    }
+    HMX_CU(h, drv.ModuleLoadData(&h->load_module, image));
+    HMX_CU(h, drv.ModuleGetFunction(&h->load_fn, h->load_module, "hmx_load"));
+    CUdeviceptr gp = 0;
+    size_t gs = 0;
+    HMX_CU(h, drv.ModuleGetGlobal(&gp, &gs, h->load_module, "hmx_load_info"));
+    HMX_CUDA(h, cudaMemcpy(h->load_info, (const void*)gp, sizeof h->load_info, cudaMemcpyDeviceToHost));
+    h->load_hash = hash;
+  }
+  if (h->load_info[0] != h->dim) return fail(h, HMX_ERR_KERNEL, "load kernel was built for dim=%d, the solver has dim=%d", h->load_info[0], h->dim);
+  if (n_cells == 0) return HMX_OK;
+  HMX_CUDA(h, h->l_qp.reserve((size_t)nq * h->dim * sizeof(double)));
+  HMX_CUDA(h, h->l_qw.reserve((size_t)nq * sizeof(double)));
+  HMX_CUDA(h, cudaMemcpyAsync(h->l_qp.p, qp, (size_t)nq * h->dim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  HMX_CUDA(h, cudaMemcpyAsync(h->l_qw.p, qw, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  struct {
+    long long n_cells;
+    const int* cell_nodes;
+    const double* node_xyz;
+    const double* qp;
+    const double* qw;
+    double* Fe;
+    int nq;
+  } P = {n_cells, cell_nodes, node_xyz, h->l_qp.as<double>(), h->l_qw.as<double>(), Fe, nq};
+  void* args[] = {&P};
+  const int threads = 128;
+  HMX_CU(h, drv.LaunchKernel(h->load_fn, (unsigned)grid_1d(n_cells, threads, h->info[6]), 1, 1, threads, 1, 1, 0, (CUstream)h->stream, args,
+                             nullptr));
   return HMX_OK;
 }
 

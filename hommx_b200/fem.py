@@ -97,8 +97,7 @@ def assemble_load(V, f):
     ``hommx_b200.ufl`` and integrated with the rule of the UFL-estimated degree."""
     msh, bs = V.mesh, V.bs
     d = msh.dim
-    x = ufl.Coordinate("x", d)
-    val = f(x)
+    val = ufl.call_traced(f, [("coord", "x", d)])
     if isinstance(val, ufl.Tensor):
         comps = [val.data[k] for k in range(val.data.shape[0])]
     elif isinstance(val, (list, tuple, np.ndarray)):

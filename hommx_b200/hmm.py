@@ -347,16 +347,42 @@ class BaseHMM:
         return self._solver.cell_tensors(points)
 
     # ------------------------------------------------------------------ solve (hmm.py:434-491)
+    def _assemble_load_device(self):
+        """Macro load vector b_i = int f . phi_i dx on the device (hmm.py:131-133, 445-450): f is
+        compiled into a small kernel (csrc/hmx_load_entry.cu), the element vectors are summed into b by the same
+        deterministic gather as the stiffness values.  Returns a device tensor (every rank assembles all of b: it is
+        outside the hot path and costs microseconds)."""
+        import torch
+
+        d = self._dev
+        tdev = d["vals"].device
+        lprog = codegen.build_load_program(self._f, self._tdim, self._bs)
+        image = native.compile_load_kernel(lprog)
+        qp, qw = quadrature.default_rule(self._tdim, lprog.degree)
+        if "b_ptr" not in d:
+            gm = assembly.build_gather(assembly.unroll_dofs(self._msh.cells, self._bs), self._num_global_dofs)
+            d["b_ptr"], d["b_src"] = torch.as_tensor(gm.ptr, device=tdev), torch.as_tensor(gm.src, device=tdev)
+            d["cells_all"] = torch.as_tensor(np.ascontiguousarray(self._msh.cells, dtype=np.int32), device=tdev)
+            d["xyz_all"] = torch.as_tensor(np.ascontiguousarray(self._msh.x), device=tdev)
+        nb = self._num_basis_functions_per_cell
+        with torch.cuda.device(self._device):
+            self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+            Fe = torch.empty((self._msh.num_cells, nb), dtype=torch.float64, device=tdev)
+            b = torch.empty(self._num_global_dofs, dtype=torch.float64, device=tdev)
+            self._solver.macro_load_dev(image, self._msh.num_cells, d["cells_all"], d["xyz_all"], qp, qw, Fe)
+            self._solver.gather_csr_dev(self._num_global_dofs, d["b_ptr"], d["b_src"], Fe, b)
+        return b
+
     def solve(self):
         self._assemble_stiffness()
-        b = fem.assemble_load(self._V_macro, self._f)
         opts = self._petsc_options_global_solve
         direct = opts.get("pc_type") == "lu" or opts.get("ksp_type") == "preonly" or opts.get("hmx_macro_solver") == "host"
         if not direct:
-            x = self._solve_on_device(b)
+            x = self._solve_on_device(self._assemble_load_device())
             if x is not None:
                 self._u.x.array[:] = x
                 return self._u
+        b = fem.assemble_load(self._V_macro, self._f)  # host path (sparse LU requested, or the device PCG did not converge)
         A = self._A.copy().tocsr()
         for bc in self._bcs:  # Dirichlet lifting, one condition at a time as in hmm.py:453-480
             u_bc = np.zeros(self._num_global_dofs)
@@ -392,7 +418,7 @@ class BaseHMM:
             d["indices"] = torch.as_tensor(self._pattern.indices, device=tdev)
         with torch.cuda.device(self._device):
             vals = torch.as_tensor(self._A_values, device=tdev).clone()  # complete values (all ranks after the halo sum)
-            t_b = torch.as_tensor(np.ascontiguousarray(b), device=tdev)
+            t_b = b.clone() if hasattr(b, "data_ptr") else torch.as_tensor(np.ascontiguousarray(b), device=tdev)
             t_x = torch.zeros(n, dtype=torch.float64, device=tdev)
             self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
             for bc in self._bcs:  # one condition at a time, each lifting with the matrix the previous ones left
@@ -498,7 +524,11 @@ class PoissonPeriodicHMM:
         self._A_hom = None
         self._correctors = None
         # the HMM machinery with a coefficient that ignores the macro point
-        self._hmm = BaseHMM(self._msh, lambda x, y: A(y), f, self._cell_mesh, eps, petsc_options_global_solve,
+        def A_xy(x, y):
+            return A(y)
+
+        A_xy.__wrapped__ = A  # lets the tracer find the UFL module A is written against
+        self._hmm = BaseHMM(self._msh, A_xy, f, self._cell_mesh, eps, petsc_options_global_solve,
                             {"ksp_rtol": float(self._petsc_options_cell_problem.get("ksp_rtol", 1e-10)),
                              "ksp_atol": float(self._petsc_options_cell_problem.get("ksp_atol", 1e-12)),
                              "ksp_max_it": int(self._petsc_options_cell_problem.get("ksp_max_it", 10000))},

@@ -31,7 +31,7 @@ _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "
 MATRIX_FREE, DENSE = 0, 3  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
-ABI_VERSION = 3  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
+ABI_VERSION = 4  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -98,6 +98,8 @@ SYMBOLS = {
     "hmx_rhs_iterations": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_macro_load_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "hmx_macro_lift_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p]),
     "hmx_macro_pcg_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -322,6 +324,43 @@ def compile_kernel(prog: CoefficientProgram, n, threads=None, force=False, keep_
     return cubin
 
 
+def compile_load_kernel(lprog, force=False):
+    """nvcc -cubin of csrc/hmx_load_entry.cu for the traced right-hand side ``lprog`` (codegen.LoadProgram); returns the
+    cubin image (bytes).  Cached in-tree like the cell kernels; NVRTC on hosts without nvcc."""
+    os.makedirs(KCACHE, exist_ok=True)
+    with open(os.path.join(CSRC, "hmx_load_entry.cu"), "rb") as f:
+        entry = f.read()
+    key = f"load{lprog.dim}_bs{lprog.bs}_{lprog.key}_{hashlib.sha1(entry).hexdigest()[:12]}"
+    cubin = os.path.join(KCACHE, key + ".cubin")
+    if not os.path.exists(cubin) or force:
+        have_nvcc = shutil.which("nvcc") is not None or os.path.exists("/usr/local/cuda/bin/nvcc")
+        uniq = f".tmp{os.getpid()}_{threading.get_ident()}"
+        if have_nvcc and os.environ.get("HMX_COMPILER", "") != "nvrtc":
+            hdr = os.path.join(KCACHE, key + uniq + ".load.cuh")
+            with open(hdr, "w") as f:
+                f.write(lprog.source)
+            cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-cubin", f'-DHMX_LOAD_FILE="{hdr}"', "-o", cubin + uniq,
+                   os.path.join(CSRC, "hmx_load_entry.cu")]  # fmt: skip
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise HmxError(f"nvcc failed for the load kernel:\n{r.stderr[-3000:]}")
+                os.replace(hdr, os.path.join(KCACHE, key + ".load.cuh"))
+                os.replace(cubin + uniq, cubin)
+            finally:
+                for leftover in (hdr, cubin + uniq):
+                    if os.path.exists(leftover):
+                        os.remove(leftover)
+        else:
+            image = _nvrtc_compile(entry.decode(), "hmx_load_entry.cu", [lprog.source.encode()], [b"hmx_load_program.cuh"],
+                                   ['-DHMX_LOAD_FILE="hmx_load_program.cuh"'])
+            with open(cubin + uniq, "wb") as f:
+                f.write(image)
+            os.replace(cubin + uniq, cubin)
+    with open(cubin, "rb") as f:
+        return f.read()
+
+
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
@@ -475,6 +514,15 @@ class CellSolver:
         self._check(self.lib.hmx_rhs_iterations(self._h, C.byref(v), 1 if reset else 0))
         return v.value
 
+    def macro_load_dev(self, image, n_cells, cell_nodes, node_xyz, qp, qw, Fe):
+        """Element load vectors Fe [n_cells][(dim+1)*bs] of the right-hand side compiled into ``image``."""
+        qp = np.ascontiguousarray(qp, dtype=np.float64)
+        qw = np.ascontiguousarray(qw, dtype=np.float64)
+        buf = C.create_string_buffer(image, len(image))
+        dp = self._dp
+        self._check(self.lib.hmx_macro_load_dev(self._h, C.cast(buf, C.c_void_p), len(image), int(n_cells), dp(cell_nodes), dp(node_xyz),
+                                                len(qw), _ptr(qp), _ptr(qw), dp(Fe)))  # fmt: skip
+
     def macro_lift_dev(self, n_dofs, indptr, indices, csr_vals, bc_mask, bc_values, b):
         dp = self._dp
         self._check(self.lib.hmx_macro_lift_dev(self._h, int(n_dofs), dp(indptr), dp(indices), dp(csr_vals), dp(bc_mask),
@@ -527,11 +575,37 @@ def _nvrtc():
     raise HmxError("neither nvcc nor libnvrtc found: the cell kernels cannot be built (there is no CPU fallback)")
 
 
+def _nvrtc_compile(src, name, headers, header_names, defines):
+    """cubin image of one translation unit compiled in-process with NVRTC for sm_100a."""
+    rt = _nvrtc()
+    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo"] + [d.encode() for d in defines]
+    prg = C.c_void_p()
+    rc = rt.nvrtcCreateProgram(C.byref(prg), src.encode(), name.encode(), len(headers),
+                               (C.c_char_p * len(headers))(*headers), (C.c_char_p * len(header_names))(*header_names))  # fmt: skip
+    if rc != 0:
+        raise HmxError(f"nvrtcCreateProgram failed ({rc})")
+    try:
+        rc = rt.nvrtcCompileProgram(prg, len(opts), (C.c_char_p * len(opts))(*opts))
+        if rc != 0:
+            size = C.c_size_t()
+            rt.nvrtcGetProgramLogSize(prg, C.byref(size))
+            log = C.create_string_buffer(size.value)
+            rt.nvrtcGetProgramLog(prg, log)
+            raise HmxError(f"NVRTC failed for {name}:\n{log.value.decode()[-4000:]}")
+        size = C.c_size_t()
+        if rt.nvrtcGetCUBINSize(prg, C.byref(size)) != 0 or size.value == 0:
+            raise HmxError("NVRTC produced no cubin")
+        image = C.create_string_buffer(size.value)
+        rt.nvrtcGetCUBIN(prg, image)
+        return image.raw
+    finally:
+        rt.nvrtcDestroyProgram(C.byref(prg))
+
+
 def compile_kernel_nvrtc(prog: CoefficientProgram, n, threads=None, min_blocks=None, variant=None, collapse=False):
     """cubin image (bytes) of the cell kernel, compiled with NVRTC for sm_100a; same source and macros as
     ``compile_kernel``."""
     threads, min_blocks, variant, coll = resolve(prog, n, threads, min_blocks, variant, collapse)
-    rt = _nvrtc()
     with open(os.path.join(CSRC, "hmx_cell_entry.cu")) as f:
         src = f.read()
     headers, names = [], []
@@ -542,28 +616,7 @@ def compile_kernel_nvrtc(prog: CoefficientProgram, n, threads=None, min_blocks=N
     headers.append(prog.source.encode())
     names.append(b"hmx_coeff_program.cuh")
     defs = kernel_defines(prog, n, threads, "hmx_coeff_program.cuh", min_blocks, variant, coll)
-    opts = [b"--gpu-architecture=sm_100a", b"-std=c++17", b"-lineinfo"] + [d.encode() for d in defs]
-    prg = C.c_void_p()
-    rc = rt.nvrtcCreateProgram(C.byref(prg), src.encode(), b"hmx_cell_entry.cu", len(headers),
-                               (C.c_char_p * len(headers))(*headers), (C.c_char_p * len(names))(*names))  # fmt: skip
-    if rc != 0:
-        raise HmxError(f"nvrtcCreateProgram failed ({rc})")
-    try:
-        rc = rt.nvrtcCompileProgram(prg, len(opts), (C.c_char_p * len(opts))(*opts))
-        if rc != 0:
-            size = C.c_size_t()
-            rt.nvrtcGetProgramLogSize(prg, C.byref(size))
-            log = C.create_string_buffer(size.value)
-            rt.nvrtcGetProgramLog(prg, log)
-            raise HmxError(f"NVRTC failed for the cell kernel:\n{log.value.decode()[-4000:]}")
-        size = C.c_size_t()
-        if rt.nvrtcGetCUBINSize(prg, C.byref(size)) != 0 or size.value == 0:
-            raise HmxError("NVRTC produced no cubin")
-        image = C.create_string_buffer(size.value)
-        rt.nvrtcGetCUBIN(prg, image)
-        return image.raw
-    finally:
-        rt.nvrtcDestroyProgram(C.byref(prg))
+    return _nvrtc_compile(src, "hmx_cell_entry.cu", headers, names, defs)
 
 
 def kernel_image(prog: CoefficientProgram, n, threads=None, min_blocks=None, variant=None, collapse=False):

@@ -536,3 +536,211 @@ def evaluate(e, env, _memo=None):
         r = _NP[e.op](*(evaluate(t, env, _memo) for t in e.args))
     _memo[e.key] = r
     return r
+
+
+# ----------------------------------------------------------------------------
+# translator from REAL UFL expression DAGs (BASELINE north star: the classes stay drop-ins for scripts that
+# `import ufl`; hmm.py:190-198 calls A(fem.Constant, ufl.SpatialCoordinate))
+# ----------------------------------------------------------------------------
+_UFL_UNARY = {"Sin": "sin", "Cos": "cos", "Tan": "tan", "Acos": "acos", "Asin": "asin", "Atan": "atan", "Sqrt": "sqrt",
+              "Exp": "exp", "Ln": "ln", "Abs": "abs"}  # fmt: skip
+_UFL_COND = {"LT": "lt", "GT": "gt", "LE": "le", "GE": "ge", "EQ": "eq", "NE": "ne"}
+
+
+def _index_id(i):
+    c = getattr(i, "count", None)
+    return c() if callable(c) else (c if c is not None else getattr(i, "_count", id(i)))
+
+
+def _multiindex(mi):
+    it = mi.indices() if callable(getattr(mi, "indices", None)) else getattr(mi, "_indices", mi)
+    return list(it)
+
+
+def from_ufl(expr, terminals):
+    """Translate a UFL expression into this module's IR (``Expr`` for a scalar, ``Tensor`` otherwise).
+
+    ``terminals`` lists ``(object, name)``: the objects the callable received -- the macro point (``fem.Constant`` of
+    shape (3,), hmm.py:190-192) as ``"x"``, the ``ufl.SpatialCoordinate`` of the micro mesh (hmm.py:186) as ``"y"``;
+    every other terminal must be a number.  The walk only uses what every UFL node offers -- the class name, ``ufl_operands``, ``ufl_shape`` -- so
+    it needs no ``import ufl`` here (and is exercised in this repository against tests/fake_ufl, a stand-in with
+    UFL's class names: UFL itself is not installable in the build image).  Covered: the operators the reference's
+    tests and examples use (arithmetic, powers, ``sin cos tan acos asin atan sqrt exp ln abs``, ``conditional`` with
+    comparisons and and/or/not, ``min_value max_value``), tensors (``as_vector as_matrix as_tensor Identity
+    transpose``), index notation (``Indexed ComponentTensor IndexSum``) and ``dot inner outer``."""
+
+    def shape(n):
+        return tuple(getattr(n, "ufl_shape", ()))
+
+    def comp(n, idx, env):
+        name = type(n).__name__
+        for t, tname in terminals:
+            if n is t:
+                return Expr("sym", (), (tname, int(idx[0])))
+        if isinstance(n, (int, float, np.integer, np.floating)):
+            return Expr.const(n)
+        ops = getattr(n, "ufl_operands", ())
+        if name in ("IntValue", "FloatValue", "RealValue", "ScalarValue", "ComplexValue"):
+            v = n.value() if callable(getattr(n, "value", None)) else getattr(n, "_value", None)
+            return Expr.const(float(v))
+        if name == "Zero":
+            return Expr.const(0.0)
+        if name == "Identity":
+            return Expr.const(1.0 if idx[0] == idx[1] else 0.0)
+        if name == "Indexed":
+            sub = []
+            for i in _multiindex(ops[1]):
+                sub.append(int(i) if type(i).__name__ == "FixedIndex" else env[_index_id(i)])
+            return comp(ops[0], tuple(sub) + tuple(idx), env)
+        if name == "ComponentTensor":
+            free = _multiindex(ops[1])
+            e2 = dict(env)
+            for i, v in zip(free, idx[: len(free)]):
+                e2[_index_id(i)] = v
+            return comp(ops[0], tuple(idx[len(free):]), e2)
+        if name == "IndexSum":
+            (i,) = _multiindex(ops[1])
+            dim = n.dimension() if callable(getattr(n, "dimension", None)) else n._dimension
+            acc = Expr.const(0.0)
+            for v in range(int(dim)):
+                e2 = dict(env)
+                e2[_index_id(i)] = v
+                acc = acc + comp(ops[0], idx, e2)
+            return acc
+        if name == "ListTensor":
+            return comp(ops[idx[0]], tuple(idx[1:]), env)
+        if name == "Transposed":
+            return comp(ops[0], (idx[1], idx[0]), env)
+        if name == "Sum":
+            return comp(ops[0], idx, env) + comp(ops[1], idx, env)
+        if name == "Product":
+            out = Expr.const(1.0)
+            for o in ops:  # at most one factor is tensor-valued
+                out = out * comp(o, idx if shape(o) else (), env)
+            return out
+        if name == "Division":
+            return comp(ops[0], idx, env) / comp(ops[1], (), env)
+        if name == "Power":
+            return comp(ops[0], (), env) ** comp(ops[1], (), env)
+        if name in _UFL_UNARY:
+            a = comp(ops[0], (), env)
+            return globals()[_UFL_UNARY[name]](a)
+        if name in _UFL_COND:
+            return Expr(_UFL_COND[name], (comp(ops[0], (), env), comp(ops[1], (), env)))
+        if name == "AndCondition":
+            return Expr("and", (comp(ops[0], (), env), comp(ops[1], (), env)))
+        if name == "OrCondition":
+            return Expr("or", (comp(ops[0], (), env), comp(ops[1], (), env)))
+        if name == "NotCondition":
+            return Expr("not", (comp(ops[0], (), env),))
+        if name == "Conditional":
+            return conditional(comp(ops[0], (), env), comp(ops[1], idx, env), comp(ops[2], idx, env))
+        if name in ("MinValue", "MaxValue"):
+            return Expr("min" if name == "MinValue" else "max", (comp(ops[0], (), env), comp(ops[1], (), env)))
+        if name in ("Dot", "Inner", "Outer"):
+            sa, sb = shape(ops[0]), shape(ops[1])
+            if name == "Outer":
+                return comp(ops[0], idx[: len(sa)], env) * comp(ops[1], idx[len(sa):], env)
+            if name == "Inner":
+                acc = Expr.const(0.0)
+                for k in np.ndindex(*sa):
+                    acc = acc + comp(ops[0], k, env) * comp(ops[1], k, env)
+                return acc
+            acc = Expr.const(0.0)
+            for k in range(sa[-1]):
+                acc = acc + comp(ops[0], tuple(idx[: len(sa) - 1]) + (k,), env) * comp(ops[1], (k,) + tuple(idx[len(sa) - 1:]), env)
+            return acc
+        raise NotImplementedError(f"UFL node {name} is not supported in coefficient expressions")
+
+    if isinstance(expr, (Expr, Tensor)):
+        return expr
+    if isinstance(expr, (int, float, np.integer, np.floating)):
+        return Expr.const(expr)
+    if isinstance(expr, (list, tuple)):
+        parts = [from_ufl(e, terminals) for e in expr]
+        return as_tensor([p.data.tolist() if isinstance(p, Tensor) else p for p in parts])
+    sh = shape(expr)
+    if not sh:
+        return comp(expr, (), {})
+    out = _obj(sh)
+    for idx in np.ndindex(*sh):
+        out[idx] = comp(expr, idx, {})
+    return Tensor(out)
+
+
+def is_foreign(val):
+    """True for an object that is not part of this module's IR but looks like a UFL expression."""
+    if isinstance(val, (Expr, Tensor, int, float, np.integer, np.floating)):
+        return False
+    return hasattr(val, "ufl_operands") or hasattr(val, "ufl_shape")
+
+
+def foreign_module(fn):
+    """The UFL-like module a user callable is written against (found in the callable's globals and closure: any module
+    other than this one that offers ``SpatialCoordinate``), or None."""
+    import types
+
+    inner = getattr(fn, "__wrapped__", None)  # PoissonPeriodicHMM wraps A(y) into A(x, y)
+    if inner is not None:
+        return foreign_module(inner)
+    seen = list(getattr(fn, "__globals__", {}).values())
+    for cell in getattr(fn, "__closure__", None) or ():
+        try:
+            seen.append(cell.cell_contents)
+        except ValueError:
+            pass
+    for v in seen:
+        if isinstance(v, types.ModuleType) and v.__name__ != __name__ and hasattr(v, "SpatialCoordinate"):
+            return v
+    return None
+
+
+def foreign_symbols(mod, dim):
+    """``(x_const, coord)`` of the foreign module, built the way the reference builds them: a (3,) ``Constant`` for the
+    macro point (hmm.py:190-192) and the ``SpatialCoordinate`` of a ``dim``-dimensional affine simplex mesh
+    (hmm.py:130, 186)."""
+    cell = {2: "triangle", 3: "tetrahedron"}[dim]
+    try:
+        import basix.ufl
+
+        element = basix.ufl.element("Lagrange", cell, 1, shape=(dim,))
+    except ImportError:
+        element = mod.VectorElement("Lagrange", cell, 1) if hasattr(mod, "VectorElement") else cell
+    domain = mod.Mesh(element)
+    return mod.Constant(domain, shape=(3,)), mod.SpatialCoordinate(domain)
+
+
+def call_traced(fn, args):
+    """Call a user callable (``A(x, y)``, ``Dtheta_transpose(x)``, ``f(x)``) and return its value in this module's IR.
+
+    ``args`` lists what each positional argument is: ``("const", name)`` for the macro point handed over as a (3,)
+    constant, ``("coord", name, dim)`` for a spatial coordinate.  The callable is first traced with this module's own
+    symbols (scripts written against ``hommx_b200.ufl``); if that raises, or the callable's module globals hold a UFL
+    module, it is called with that module's ``Constant`` / ``SpatialCoordinate`` and the resulting UFL DAG is translated
+    (``from_ufl``)."""
+    own = [Coordinate(a[1], 3 if a[0] == "const" else a[2]) for a in args]
+    mod = foreign_module(fn)
+    first = None
+    if mod is None:
+        val = fn(*own)
+        if not is_foreign(val):
+            return val
+        raise TypeError(f"the callable returned a {type(val).__name__}: write it against hommx_b200.ufl or UFL")
+    try:
+        val = fn(*own)
+        if not is_foreign(val) and not (isinstance(val, (list, tuple)) and any(is_foreign(v) for v in val)):
+            return val
+    except Exception as e:  # UFL rejects this module's symbols (as_ufl): trace with its own
+        first = e
+    syms, terminals = [], []
+    for a in args:
+        dim = 3 if a[0] == "const" else a[2]
+        xc, yc = foreign_symbols(mod, dim)
+        s = xc if a[0] == "const" else yc
+        syms.append(s)
+        terminals.append((s, a[1]))
+    try:
+        val = fn(*syms)
+    except Exception as e:
+        raise e from first
+    return from_ufl(val, terminals)

@@ -31,7 +31,7 @@ typedef struct hmx_handle hmx_t;
 /* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
  * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
  * to new Python sources would otherwise be called with the wrong arguments). */
-#define HMX_ABI_VERSION 3
+#define HMX_ABI_VERSION 4
 int32_t hmx_abi_version(void);
 
 enum hmx_status {
@@ -128,6 +128,16 @@ int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset);
  * back.  All pointers are device pointers. */
 int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, int64_t n, double* buf);
 int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_t n, const double* buf);
+
+/* the macro load vector on the device.  Replaces the FFCx kernel behind
+ * `_assemble_vector_array(b_local.array_w, self._L, ...)` (hmm.py:445-450; L = inner(f(x), v) dx, hmm.py:131-133).
+ * `image` is the cubin of csrc/hmx_load_entry.cu specialised for f (hommx_b200.codegen.build_load_program); qp [nq][dim]
+ * / qw [nq] is the quadrature rule of the UFL-estimated degree on the reference simplex (HOST pointers, tiny).  Writes
+ * the element vectors Fe [n_cells][(dim+1)*bs] (device); b is then their deterministic gather:
+ * hmx_gather_csr_dev(h, n_dofs, ptr, src, Fe, b) with the gather map of the dof numbering.  cell_nodes / node_xyz / Fe
+ * are device pointers; work is enqueued on the handle's stream. */
+int hmx_macro_load_dev(hmx_t* h, const void* image, size_t image_size, int64_t n_cells, const int32_t* cell_nodes,
+                       const double* node_xyz, int32_t nq, const double* qp, const double* qw, double* Fe);
 
 /* SURVEY 8f rows 2-3 (outside the north-star hot path; the reference does this with PETSc, hmm.py:453-491):
  * Dirichlet lifting on the device -- b -= A u_bc on the free rows, constrained rows and columns zeroed with a unit

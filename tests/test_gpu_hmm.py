@@ -230,3 +230,30 @@ def test_device_macro_solve_matches_host_solve():
         s.set_boundary_conditions(fem.dirichletbc(np.zeros(3), clamp, s.function_space))
     ua, ub = a.solve(), b.solve()
     assert np.abs(ua.x.array - ub.x.array).max() <= 1e-8 * np.abs(ub.x.array).max()
+
+
+@pytest.mark.parametrize("dim,bs", [(2, 1), (3, 1), (3, 3)])
+def test_device_load_vector_matches_host_assembly(dim, bs):
+    """SURVEY 8f row 2 / hmm.py:445-450: the macro load vector assembled on the device (generated f kernel +
+    deterministic gather, hmx_macro_load_dev) against the host assembly of hommx_b200.fem."""
+    from hommx_b200 import fem
+
+    if dim == 2:
+        m, mic = mesh.create_rectangle((0.0, 0.0), (1.0, 0.7), (9, 7)), mesh.create_unit_square(4, 4)
+        f = lambda x: 1.0 + pufl.sin(3 * x[0]) * x[1] ** 2  # noqa: E731
+        s = PoissonHMM(m, Cf.smooth_sin(pufl), f, mic, 0.1)
+    elif bs == 1:
+        m, mic = mesh.create_box((0.0, 0.0, 0.0), (1.0, 0.5, 0.3), (5, 4, 3)), mesh.create_unit_cube(4, 4, 4)
+        f = lambda x: pufl.cos(x[0] + 2 * x[2]) + x[1]  # noqa: E731
+        s = PoissonHMM(m, Cf.smooth_sin(pufl), f, mic, 0.1)
+    else:
+        m, mic = mesh.create_box((0.0, 0.0, 0.0), (1.0, 0.4, 0.1), (6, 3, 2)), mesh.create_unit_cube(4, 4, 4)
+        f = lambda x: pufl.as_vector([0.0, x[0] * pufl.sin(x[1]), -0.05 * 0.4**2])  # noqa: E731
+        s = LinearElasticityHMM(m, Cf.hooke_smooth_3d(pufl), f, mic, 0.1)
+    s._ensure_solver()
+    b_dev = s._assemble_load_device().cpu().numpy()
+    b_host = fem.assemble_load(s._V_macro, f)
+    assert np.abs(b_dev - b_host).max() <= 1e-13 * np.abs(b_host).max()
+    s.set_right_hand_side(lambda x: 2.0 if bs == 1 else pufl.as_vector([1.0, 0.0, 0.0]))  # a new f loads a new module
+    b2 = s._assemble_load_device().cpu().numpy()
+    assert np.abs(b2 - fem.assemble_load(s._V_macro, s._f)).max() <= 1e-13 * np.abs(b2).max()
