@@ -26,6 +26,10 @@
 #include "hmx_cell_common.cuh"
 #include "hmx_cell_coarse.cuh"
 
+#ifndef HMX_STAGGER
+#define HMX_STAGGER 0  // SM clocks between the PCG starts of consecutive right-hand-side groups
+#endif
+
 namespace hmx {
 
 // VGLOB = 1: the search directions p and the product y = K p live in the L2-resident scratch instead of
@@ -757,6 +761,13 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
     int it = 0;
     bool active = rz0 > P.atol * P.atol;
     const double tol2 = fmax(P.rtol * P.rtol * rz0, P.atol * P.atol);
+#if HMX_STAGGER > 0
+    // The groups start in lock step and every iteration costs each of them the same, so without this they all sweep
+    // (FP64 pipe saturated) and then all sit in their latency-bound phases (reductions, coarse correction: pipe idle)
+    // at the same time.  Offsetting group q by q / NRHS of an iteration lets one group's bubbles fill with the
+    // others' sweeps for the whole solve; costs < 1 % of a cell once.
+    if (!L::SUBW) spin_cycles((long long)q * HMX_STAGGER);
+#endif
     // SUBW: the right-hand sides sharing a warp loop together (the converged ones only keep y clean)
     while (L::SUBW ? warp_any(active && it < P.max_it) : (active && it < P.max_it)) {
       const bool mine = active && it < P.max_it;

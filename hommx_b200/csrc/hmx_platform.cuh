@@ -15,6 +15,8 @@
 #define HMX_DEV __device__ __forceinline__
 #define HMX_HOSTDEV __host__ __device__ __forceinline__
 #define HMX_GLOBAL(maxthreads, minblocks) __global__ void __launch_bounds__(maxthreads, minblocks)
+// a kernel launched as thread-block clusters of `cl` CTAs (compile-time cluster size: a plain launch forms the clusters)
+#define HMX_GLOBAL_CLUSTER(maxthreads, cl) __global__ void __cluster_dims__(cl, 1, 1) __launch_bounds__(maxthreads, 1)
 #define HMX_RESTRICT __restrict__
 #define HMX_UNROLL _Pragma("unroll")
 
@@ -117,6 +119,44 @@ HMX_DEV double fast_rsqrt(double x) {
   }
   return r;
 }
+// ---- thread-block clusters + distributed shared memory ----
+HMX_DEV int cluster_rank() {  // %cluster_ctarank: this CTA's rank in its cluster
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return (int)r;
+}
+HMX_DEV int cluster_id() {  // %clusterid.x
+  unsigned r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return (int)r;
+}
+HMX_DEV int nclusters() {  // %nclusterid.x
+  unsigned r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return (int)r;
+}
+// split cluster barrier (UCGABAR_ARV / UCGABAR_WAIT): arrive releases this thread's earlier writes -- also those into
+// other CTAs' shared memory -- to the cluster, wait acquires everybody else's.  Every thread of every CTA calls both.
+HMX_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+HMX_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+HMX_DEV void cluster_sync() {
+  cluster_arrive();
+  cluster_wait();
+}
+// generic address of the same shared-memory location in the CTA of rank `rank` (mapa): plain loads / stores through it
+// travel over the SM-to-SM network (DSMEM)
+template <class T>
+HMX_DEV T* cluster_map(T* p, int rank) {
+  unsigned long long out;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+  return reinterpret_cast<T*>(out);
+}
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
+// busy-wait for about `cycles` SM clocks (CS2R on the clock register): staggers the right-hand-side groups of a CTA
+HMX_DEV void spin_cycles(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {
+  }
+}
 }  // namespace hmx
 #endif

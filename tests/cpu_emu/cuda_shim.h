@@ -17,11 +17,21 @@
 #define __device__
 #define __forceinline__ inline
 #define HMX_GLOBAL(maxthreads, minblocks) void
+#define HMX_GLOBAL_CLUSTER(maxthreads, cl) void
 
 namespace hmx {
 namespace emu {
+struct ClusterState {
+  int arrived = 0;
+  unsigned gen = 0;
+};
 struct Cta {
   int nthreads, bid, nblocks, cur;
+  // thread-block cluster this CTA belongs to (size 1 for ordinary launches): its CTAs' fibers run in one scheduler
+  int crank = 0, csize = 1, fiber_base = 0;
+  Cta* peers = nullptr;           // [csize] the CTAs of the cluster, by rank
+  ClusterState* cluster = nullptr;
+  unsigned* cgen = nullptr;       // [nthreads] barrier generation each fiber arrived in
   double* smem;
   double* wbuf;  // [2][nthreads] warp collective exchange
   int* wpar;     // [nthreads] per-fiber parity
@@ -153,5 +163,32 @@ inline void mbar_inval(MBar*) {}
 inline void fence_async_proxy() {}
 inline double fast_div(double a, double b) { return a / b; }
 inline double fast_rsqrt(double x) { return 1.0 / sqrt(x); }
+// ---- clusters: a cluster's CTAs live in one address space here, DSMEM is a pointer into the peer's buffer ----
+inline int cluster_rank() { return emu::g_cta->crank; }
+inline int cluster_id() { return emu::g_cta->bid / emu::g_cta->csize; }
+inline int nclusters() { return emu::g_cta->nblocks / emu::g_cta->csize; }
+inline void cluster_arrive() {
+  emu::Cta* c = emu::g_cta;
+  c->cgen[c->cur] = c->cluster->gen;
+  if (++c->cluster->arrived == c->csize * c->nthreads) {
+    c->cluster->arrived = 0;
+    ++c->cluster->gen;
+  }
+}
+inline void cluster_wait() {
+  emu::Cta* c = emu::g_cta;
+  while (c->cluster->gen == c->cgen[c->cur]) emu::yield();
+}
+inline void cluster_sync() {
+  cluster_arrive();
+  cluster_wait();
+}
+template <class T>
+inline T* cluster_map(T* p, int rank) {
+  emu::Cta* c = emu::g_cta;
+  const size_t off = (size_t)((const char*)p - (const char*)c->smem);
+  return reinterpret_cast<T*>((char*)c->peers[rank].smem + off);
+}
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline void spin_cycles(long long) {}  // timing only: nothing to emulate
 }  // namespace hmx
