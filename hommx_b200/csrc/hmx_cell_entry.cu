@@ -5,7 +5,13 @@
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
 #ifndef HMX_VARIANT
-#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel (PCG), 3 = dense Cholesky
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel (PCG), 3 = dense Cholesky, 4 = cluster-resident stencil
+#endif
+#ifndef HMX_CLUSTER
+#define HMX_CLUSTER 1  // CTAs per thread-block cluster (variant 4: the cell is split into z-slabs over the cluster)
+#endif
+#ifndef HMX_TPN
+#define HMX_TPN 2  // variant 4: threads per node
 #endif
 // (variants 1 and 2 -- the assembled operator streamed from L2, barrier- or TMA-staged -- were measured slower than
 // variant 0 and live in experiments/assembled_operator/; they build only with -DHMX_EXPERIMENTAL_VARIANTS and that
@@ -19,6 +25,9 @@
 #include "hmx_cell_elasticity_tma.cuh"
 #endif
 #include "hmx_cell_dense.cuh"
+#if HMX_VARIANT == 4
+#include "hmx_cell_cluster.cuh"
+#endif
 #endif
 #include HMX_COEFF_FILE
 
@@ -41,19 +50,28 @@ using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 using Layout = hmx::ElasticityTmaLayout<HMX_COEFF, HMX_NM, HMX_NT>;
 #elif HMX_VARIANT == 3
 using Layout = hmx::DenseLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>;
+#elif HMX_VARIANT == 4
+using Layout = hmx::ClusterLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_CLUSTER, HMX_TPN>;
 #else
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #endif
 #ifndef HMX_EXPERIMENTAL_VARIANTS
-static_assert(HMX_KIND == 0 || HMX_VARIANT == 0 || HMX_VARIANT == 3, "elasticity kernel variants: 0 (matrix-free PCG) or 3 (dense Cholesky)");
+static_assert(HMX_KIND == 0 || HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_VARIANT == 4,
+              "elasticity kernel variants: 0 (matrix-free PCG), 3 (dense Cholesky) or 4 (cluster-resident stencil)");
 #endif
-static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled variant has no collapsed form");
+static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled variants have no collapsed form");
+static_assert(HMX_VARIANT == 4 || HMX_CLUSTER == 1, "only variant 4 is launched as thread-block clusters");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
 constexpr int kSmemBytes = Layout::total * 8;
 constexpr int kScratch = Layout::scratch_doubles;
 }  // namespace
 
 #ifndef HMX_EMULATE
+#if HMX_VARIANT == 4
+extern "C" HMX_GLOBAL_CLUSTER(HMX_NT, HMX_CLUSTER) hmx_cell(const hmx::CellParams P) {
+  hmx::elasticity_cluster_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_CLUSTER, HMX_TPN>(P);
+}
+#else
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 #if HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
@@ -67,9 +85,11 @@ extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
 }
-// 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree
-extern "C" __device__ const int hmx_info[8] = {kSmemBytes, HMX_NT,  Layout::NRHS, HMX_COEFF::DIM,
-                                               HMX_KIND,   HMX_NM,  kScratch,     HMX_COEFF::QDEG};
+#endif
+// 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree,
+// 8 CTAs per cluster (1: ordinary launch; the grid must be a multiple of it), 9-11 reserved
+extern "C" __device__ const int hmx_info[12] = {kSmemBytes, HMX_NT, Layout::NRHS, HMX_COEFF::DIM, HMX_KIND, HMX_NM,
+                                                kScratch, HMX_COEFF::QDEG, HMX_CLUSTER, 0, 0, 0};
 #else
 #include "emu_runtime.h"
 static void emu_body(void* arg) {
@@ -82,15 +102,18 @@ static void emu_body(void* arg) {
   hmx::elasticity_tma_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
 #elif HMX_VARIANT == 3
   hmx::elasticity_dense_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL>(P);
+#elif HMX_VARIANT == 4
+  hmx::elasticity_cluster_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_CLUSTER, HMX_TPN>(P);
 #else
   hmx::elasticity_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #endif
 }
+extern "C" int hmx_emu_cluster() { return HMX_CLUSTER; }
 extern "C" void hmx_emu_info(int* out) {
   const int v[8] = {kSmemBytes, HMX_NT, Layout::NRHS, HMX_COEFF::DIM, HMX_KIND, HMX_NM, kScratch, HMX_COEFF::QDEG};
   for (int i = 0; i < 8; ++i) out[i] = v[i];
 }
 extern "C" void hmx_emu_launch(hmx::CellParams* P, int grid, int host_threads) {
-  hmx::emu::run_grid(grid, HMX_NT, (size_t)Layout::total, emu_body, P, host_threads);
+  hmx::emu::run_grid(grid, HMX_NT, (size_t)Layout::total, emu_body, P, host_threads, HMX_CLUSTER);
 }
 #endif

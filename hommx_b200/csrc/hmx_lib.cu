@@ -159,6 +159,7 @@ struct Driver {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                            void**, void**) = nullptr;
   CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+  CUresult (*OccupancyMaxActiveClusters)(int*, CUfunction, const CUlaunchConfig*) = nullptr;
   CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
   bool ok = false;
   std::string why;
@@ -185,6 +186,7 @@ Driver& driver() {
            load_entry("cuModuleGetGlobal", d.ModuleGetGlobal, d.why) &&
            load_entry("cuFuncSetAttribute", d.FuncSetAttribute, d.why) && load_entry("cuLaunchKernel", d.LaunchKernel, d.why) &&
            load_entry("cuOccupancyMaxActiveBlocksPerMultiprocessor", d.OccupancyMaxActiveBlocksPerMultiprocessor, d.why) &&
+           load_entry("cuOccupancyMaxActiveClusters", d.OccupancyMaxActiveClusters, d.why) &&
            load_entry("cuGetErrorString", d.GetErrorString, d.why);
   }
   return d;
@@ -234,6 +236,8 @@ struct hmx_handle {
   double rtol = 1e-8, atol = 1e-10;
   int max_it = 10000;
   int info[8] = {0};
+  int cluster = 1;       // CTAs per thread-block cluster of the cell kernel (hmx_info[8]; 1: ordinary launch)
+  int max_clusters = 0;  // clusters of the cell kernel that are resident at once
   int grid_override = 0;
   CUmodule module = nullptr;
   CUfunction fn = nullptr;
@@ -300,6 +304,11 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
   long long grid = (long long)per_sm * sms;
   if (h->grid_override > 0) grid = h->grid_override;
   grid = std::max<long long>(1, std::min<long long>(grid, n_pts));
+  if (h->cluster > 1) {  // one macro point per cluster: a whole number of clusters, at most the resident ones
+    long long ncl = h->grid_override > 0 ? std::max<long long>(1, h->grid_override / h->cluster) : h->max_clusters;
+    ncl = std::max<long long>(1, std::min<long long>(ncl, n_pts));
+    grid = ncl * h->cluster;
+  }
   const size_t scratch_doubles = (size_t)h->info[7] * (size_t)grid;
   if (scratch_doubles) HMX_CUDA(h, h->scratch.reserve(scratch_doubles * sizeof(double)));
   hmx::CellParams P;
@@ -389,8 +398,8 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
       fail(h, HMX_ERR_KERNEL, "kernel image has no 'hmx_info' table");
       return bail(HMX_ERR_KERNEL);
     }
-    int ki[8];
-    if (cudaMemcpy(ki, (const void*)gp, sizeof ki, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    int ki[12] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+    if (cudaMemcpy(ki, (const void*)gp, std::min(gs, sizeof ki), cudaMemcpyDeviceToHost) != cudaSuccess) {
       fail(h, HMX_ERR_CUDA, "reading hmx_info failed: %s", cudaGetErrorString(cudaGetLastError()));
       return bail(HMX_ERR_CUDA);
     }
@@ -418,6 +427,38 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
       return bail(HMX_ERR_KERNEL);
     }
     h->info[5] = per_sm;
+    h->cluster = ki[8] > 1 ? ki[8] : 1;
+    if (h->cluster > 1) {
+      // the kernel carries its cluster size (__cluster_dims__): a plain launch of a multiple of it forms the clusters
+      if (h->cluster > 8) {
+        r = drv.FuncSetAttribute(h->fn, CU_FUNC_ATTRIBUTE_NON_PORTABLE_CLUSTER_SIZE_ALLOWED, 1);
+        if (r != CUDA_SUCCESS) {
+          fail(h, HMX_ERR_KERNEL, "cell kernel needs clusters of %d CTAs: not available on this device", h->cluster);
+          return bail(HMX_ERR_KERNEL);
+        }
+      }
+      CUlaunchAttribute attr;
+      attr.id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+      attr.value.clusterDim.x = (unsigned)h->cluster;
+      attr.value.clusterDim.y = 1;
+      attr.value.clusterDim.z = 1;
+      CUlaunchConfig cfg;
+      std::memset(&cfg, 0, sizeof cfg);
+      cfg.gridDimX = (unsigned)h->cluster;
+      cfg.gridDimY = cfg.gridDimZ = 1;
+      cfg.blockDimX = (unsigned)ki[1];
+      cfg.blockDimY = cfg.blockDimZ = 1;
+      cfg.sharedMemBytes = (unsigned)ki[0];
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      int ncl = 0;
+      r = drv.OccupancyMaxActiveClusters(&ncl, h->fn, &cfg);
+      if (r != CUDA_SUCCESS || ncl < 1) {
+        fail(h, HMX_ERR_KERNEL, "no cluster of %d CTAs (threads=%d smem=%d) can be resident on this device", h->cluster, ki[1], ki[0]);
+        return bail(HMX_ERR_KERNEL);
+      }
+      h->max_clusters = ncl;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, d->device) != cudaSuccess) {
       fail(h, HMX_ERR_CUDA, "cudaGetDeviceProperties failed");
@@ -481,6 +522,13 @@ int hmx_set_tolerances(hmx_t* h, double rtol, double atol, int32_t max_it) {
 int hmx_set_grid(hmx_t* h, int32_t n) {
   if (!h || n < 0) return HMX_ERR_ARG;
   h->grid_override = n;
+  return HMX_OK;
+}
+
+int hmx_cluster_info(const hmx_t* h, int32_t info[2]) {
+  if (!h || !info) return HMX_ERR_ARG;
+  info[0] = h->cluster;
+  info[1] = h->cluster > 1 ? h->max_clusters : 0;
   return HMX_OK;
 }
 

@@ -27,11 +27,11 @@ KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_coarse.cuh", "hmx_cell_elasticity.cuh",
-            "hmx_cell_dense.cuh", "hmx_cell_entry.cu")
-MATRIX_FREE, DENSE = 0, 3  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
+            "hmx_cell_dense.cuh", "hmx_cell_cluster.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, DENSE, CLUSTER = 0, 3, 4  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
-ABI_VERSION = 4  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
+ABI_VERSION = 5  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -95,6 +95,7 @@ SYMBOLS = {
     "hmx_assemble_macro_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_gather_csr_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmx_cluster_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "hmx_rhs_iterations": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -164,6 +165,61 @@ def collapse_mask(prog, collapse=True):
     if not collapse:
         return 0
     return ~prog.ydep & ((1 << prog.dim) - 1)
+
+
+def cluster_tpn():
+    """Threads per node of the cluster kernel (2: each thread owns half of the right-hand sides)."""
+    return int(os.environ.get("HMX_TPN", "2"))
+
+
+def cluster_coarse_dofs(prog, n, threads=512):
+    """Unknowns of the cluster kernel's coarse space (mirrors ``ClusterLayout::TWO`` in csrc/hmx_cell_cluster.cuh): the
+    level-1 space summed along micro axis 0 when the coefficient does not depend on it; 0 = block Jacobi only."""
+    if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" or n % 2 or n < 4 or threads // 6 < 32:
+        return 0
+    h = n // 2
+    if 3 * h**3 <= 96 or (prog.ydep & 1):
+        return 0
+    return 3 * h * h if 3 * h * h <= 96 else 0
+
+
+def cluster_threads(prog, n, cl):
+    own = (n // cl) * n * n * cluster_tpn()
+    nt = 32 * (-(-own // 32))
+    ncd = cluster_coarse_dofs(prog, n)
+    return max(nt, 64, 32 * (-(-(6 * ncd + 6) // 32)) if ncd else 0)
+
+
+def cluster_smem_bytes(prog, n, cl):
+    """Shared memory per CTA of the cluster kernel (mirrors ``ClusterLayout``)."""
+    nt = cluster_threads(prog, n, cl)
+    pz, npl = n // cl, n * n
+    nown, npb = pz * npl, (pz + 2) * npl
+    ncd = cluster_coarse_dofs(prog, n, nt) or 2
+    two = cluster_coarse_dofs(prog, n, nt) > 0
+    nrec = (max(6 * ncd + 6, 36) + 1) // 2 * 2
+    nblk = (ncd + 31) // 32
+    cbuf = 0
+    if two:
+        pad = max((ncd + 15) // 16 * 16, -(-ncd // (nt // 16)) * (nt // 16))
+        cbuf = max(3 * pad + 2, 6 * ncd) + 2
+    work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36)
+    ntri = ncd * (ncd + 1) // 2 if two else 0
+    doubles = (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
+    return 8 * doubles
+
+
+def cluster_size(prog, n):
+    """CTAs per cluster of the cluster kernel: the smallest split of the cell into z-slabs whose share of the stencil
+    fits in 227 KB (8^3: 2, 10^3: 5); ``HMX_CLUSTER_SIZE`` overrides.  0: the cell cannot be split (n has no divisor
+    <= 16 that fits)."""
+    forced = os.environ.get("HMX_CLUSTER_SIZE")
+    if forced:
+        return int(forced)
+    for cl in range(2, 17):
+        if n % cl == 0 and cluster_threads(prog, n, cl) <= 1024 and cluster_smem_bytes(prog, n, cl) <= SMEM_LIMIT:
+            return cl
+    return 0
 
 
 def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
@@ -243,7 +299,7 @@ def precond_mode(prog, variant=MATRIX_FREE):
     """1: the matrix-free elasticity kernel is built with the additive two-level preconditioner (block Jacobi + an
     exactly inverted Galerkin coarse matrix, csrc/hmx_cell_coarse.cuh) wherever its coarse space fits next to the
     vectors (the kernel decides: ``CoarseSpace::ON``); 0: block Jacobi only (``HMX_PRECOND=jacobi``)."""
-    if prog.kind == POISSON or variant != MATRIX_FREE:
+    if prog.kind == POISSON or variant not in (MATRIX_FREE, CLUSTER):
         return 0
     return 0 if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" else 1
 
@@ -266,14 +322,16 @@ def coarse_dofs(prog, n, variant=MATRIX_FREE, coll=0):
 def kernel_key(prog: CoefficientProgram, n, threads, min_blocks=1, variant=MATRIX_FREE, coll=0):
     kind = "p" if prog.kind == POISSON else "e"
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
-    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}c{coll}g{vg}p{precond_mode(prog, variant)}_{prog.key}_{_src_hash()}"
+    cl = f"k{cluster_size(prog, n)}x{cluster_tpn()}" if variant == CLUSTER else ""
+    return f"{kind}{prog.dim}_n{n}_t{threads}b{min_blocks}v{variant}{cl}c{coll}g{vg}p{precond_mode(prog, variant)}_{prog.key}_{_src_hash()}"
 
 
 def kernel_defines(prog, n, threads, coeff_path, min_blocks=1, variant=MATRIX_FREE, coll=0):
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
+    cl = [f"-DHMX_CLUSTER={cluster_size(prog, n)}", f"-DHMX_TPN={cluster_tpn()}"] if variant == CLUSTER else []
     return [f'-DHMX_COEFF_FILE="{coeff_path}"', f"-DHMX_KIND={prog.kind}", f"-DHMX_NM={n}", f"-DHMX_NT={threads}",
             f"-DHMX_MINB={min_blocks}", f"-DHMX_VARIANT={variant}", f"-DHMX_COLL={coll}", f"-DHMX_VGLOB={vg}",
-            f"-DHMX_PRECOND={precond_mode(prog, variant)}"]  # fmt: skip
+            f"-DHMX_PRECOND={precond_mode(prog, variant)}", *cl]  # fmt: skip
 
 
 def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False):
@@ -281,6 +339,13 @@ def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False
     coll = collapse_mask(prog, collapse) if variant in (MATRIX_FREE, DENSE) else 0
     if variant == DENSE and not dense_fits(prog, n, coll):
         raise HmxError(f"the dense variant holds at most {DENSE_MAX_DOF} unknowns per cell")
+    if variant == CLUSTER:
+        if prog.kind == POISSON or prog.dim != 3:
+            raise HmxError("the cluster variant is the 3-D elasticity kernel")
+        cl = cluster_size(prog, n)
+        if cl < 2 or n % cl:
+            raise HmxError(f"an {n}^3 cell cannot be split into z-slabs over a thread-block cluster")
+        return threads or cluster_threads(prog, n, cl), 1, variant, 0
     threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll)
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
     min_blocks = min_blocks or (1 if variant == DENSE else default_min_blocks(prog.dim, prog.kind, n, threads, coll, vg))
@@ -403,6 +468,9 @@ class CellSolver:
         info = (C.c_int32 * 8)()
         self._check(self.lib.hmx_kernel_info(self._h, info))
         self.info = dict(zip(("smem_bytes", "threads", "n_rhs", "m", "n_b", "ctas_per_sm", "sms", "scratch_doubles"), info))
+        cinfo = (C.c_int32 * 2)()
+        self._check(self.lib.hmx_cluster_info(self._h, cinfo))
+        self.info["cluster"], self.info["resident_clusters"] = int(cinfo[0]), int(cinfo[1])
 
     # -- plumbing ----------------------------------------------------------------
     def _check(self, rc):

@@ -31,7 +31,7 @@ typedef struct hmx_handle hmx_t;
 /* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
  * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
  * to new Python sources would otherwise be called with the wrong arguments). */
-#define HMX_ABI_VERSION 4
+#define HMX_ABI_VERSION 5
 int32_t hmx_abi_version(void);
 
 enum hmx_status {
@@ -81,6 +81,10 @@ int hmx_set_grid(hmx_t* h, int32_t n_ctas);
  * [2]=right-hand sides per point, [3]=m (A_hom is m x m), [4]=n_b (S_loc is n_b x n_b),
  * [5]=CTAs per SM, [6]=SM count, [7]=per-CTA scratch doubles */
 int hmx_kernel_info(const hmx_t* h, int32_t info[8]);
+/* thread-block clusters of the loaded kernel: info[0]=CTAs per cluster (1: ordinary launch; > 1: the cluster variant of
+ * the 3-D elasticity kernel, csrc/hmx_cell_cluster.cuh -- one macro point per cluster, the assembled stencil resident
+ * in the cluster's distributed shared memory), info[1]=clusters resident on the device at once (= the grid launched) */
+int hmx_cluster_info(const hmx_t* h, int32_t info[2]);
 
 /* Homogenised tensors at given macro points: replaces the n_b corrector solves and n_b^2
  * assemble_scalar calls of _compute_local_stiffness (hmm.py:354-364) in the d-RHS form of

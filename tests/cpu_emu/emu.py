@@ -49,6 +49,7 @@ def build(prog, n, threads=None, variant=None, collapse=False):
     lib = C.CDLL(so)
     lib.hmx_emu_launch.argtypes = [C.POINTER(CellParams), C.c_int, C.c_int]
     lib.hmx_emu_info.argtypes = [C.POINTER(C.c_int)]
+    lib.hmx_emu_cluster.restype = C.c_int
     return lib
 
 
@@ -69,7 +70,8 @@ class EmuSolver:
         self.nb = (prog.dim + 1) * (1 if prog.kind == 0 else prog.dim)
 
     def _launch(self, P, n):
-        grid = max(1, min(self.grid, n))
+        cl = self.lib.hmx_emu_cluster()  # CTAs per thread-block cluster (1: ordinary launch)
+        grid = cl * max(1, min(self.grid // cl if cl > 1 else self.grid, n))
         scratch = np.zeros(max(1, self.info[6] * grid))
         P.scratch = scratch.ctypes.data
         P.qp, P.qw, P.nq = self.qp.ctypes.data, self.qw.ctypes.data, len(self.qw)

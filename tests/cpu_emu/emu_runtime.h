@@ -25,26 +25,21 @@ thread_local Sched* g_sched = nullptr;
 
 void yield() {
   Sched* s = g_sched;
-  swapcontext(&s->ctx[g_cta->cur], &s->main_ctx);
+  swapcontext(&s->ctx[g_cta->fiber_base + g_cta->cur], &s->main_ctx);
 }
 
 static void fiber_entry() {
   Sched* s = g_sched;
   s->body(s->arg);
-  s->done[g_cta->cur] = 1;
-  swapcontext(&s->ctx[g_cta->cur], &s->main_ctx);
+  s->done[g_cta->fiber_base + g_cta->cur] = 1;
+  swapcontext(&s->ctx[g_cta->fiber_base + g_cta->cur], &s->main_ctx);
 }
 
-// run one CTA: nthreads fibers over `body`
-inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, void (*body)(void*), void* arg) {
+// run one thread-block cluster (csize CTAs of nthreads fibers each, one scheduler, one address space); csize = 1 is
+// an ordinary CTA.  bid0 = block index of rank 0.
+inline void run_cluster(int csize, int nthreads, int bid0, int nblocks, size_t smem_doubles, void (*body)(void*), void* arg) {
   constexpr size_t STACK = 256 * 1024;
-  Cta cta;
-  cta.nthreads = nthreads;
-  cta.bid = bid;
-  cta.nblocks = nblocks;
-  cta.cur = 0;
-  std::memset(cta.arrived, 0, sizeof cta.arrived);
-  std::memset(cta.gen, 0, sizeof cta.gen);
+  const int nfib = csize * nthreads;
   // shared memory is NOT zero-initialised on the device: HMX_EMU_POISON=1 fills it with NaNs (0xfff7... bit
   // patterns, huge as integers) so that a read of a slot nobody wrote shows up as a NaN result or a wild index
   const char* poison = std::getenv("HMX_EMU_POISON");
@@ -53,20 +48,41 @@ inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, voi
     const unsigned long long bits = 0xfff7dead7ff7beefULL;
     std::memcpy(&fill, &bits, sizeof fill);
   }
-  std::vector<double> smem(smem_doubles + 2, fill), wbuf(2 * nthreads, 0.0);
-  std::vector<int> wpar(nthreads, 0);
-  cta.smem = smem.data();
-  cta.wbuf = wbuf.data();
-  cta.wpar = wpar.data();
+  std::vector<Cta> ctas(csize);
+  std::vector<std::vector<double>> smem(csize), wbuf(csize);
+  std::vector<std::vector<int>> wpar(csize);
+  std::vector<std::vector<unsigned>> cgen(csize);
+  ClusterState cstate;
+  for (int r = 0; r < csize; ++r) {
+    Cta& cta = ctas[r];
+    cta.nthreads = nthreads;
+    cta.bid = bid0 + r;
+    cta.nblocks = nblocks;
+    cta.cur = 0;
+    cta.crank = r;
+    cta.csize = csize;
+    cta.fiber_base = r * nthreads;
+    cta.peers = ctas.data();
+    cta.cluster = &cstate;
+    std::memset(cta.arrived, 0, sizeof cta.arrived);
+    std::memset(cta.gen, 0, sizeof cta.gen);
+    smem[r].assign(smem_doubles + 2, fill);
+    wbuf[r].assign(2 * nthreads, 0.0);
+    wpar[r].assign(nthreads, 0);
+    cgen[r].assign(nthreads, 0u);
+    cta.smem = smem[r].data();
+    cta.wbuf = wbuf[r].data();
+    cta.wpar = wpar[r].data();
+    cta.cgen = cgen[r].data();
+  }
   Sched s;
   s.body = body;
   s.arg = arg;
-  s.ctx.resize(nthreads);
-  s.done.assign(nthreads, 0);
-  s.stacks.resize(nthreads);
-  g_cta = &cta;
+  s.ctx.resize(nfib);
+  s.done.assign(nfib, 0);
+  s.stacks.resize(nfib);
   g_sched = &s;
-  for (int t = 0; t < nthreads; ++t) {
+  for (int t = 0; t < nfib; ++t) {
     s.stacks[t] = (char*)std::malloc(STACK);
     getcontext(&s.ctx[t]);
     s.ctx[t].uc_stack.ss_sp = s.stacks[t];
@@ -77,46 +93,49 @@ inline void run_cta(int nthreads, int bid, int nblocks, size_t smem_doubles, voi
   // Scheduling order of the fibers between barriers.  A kernel without data races gives bit-identical results
   // under every order (tests/test_emu_parity.py::test_results_do_not_depend_on_the_thread_schedule):
   //   HMX_EMU_ORDER unset / "forward": 0, 1, 2, ...   "reverse": n-1, ..., 0   "shuffle:<seed>": a new random
-  //   permutation in every round
+  //   permutation in every round  (for a cluster the order runs over the fibers of all its CTAs)
   const char* mode = std::getenv("HMX_EMU_ORDER");
   const bool reverse = mode != nullptr && std::strcmp(mode, "reverse") == 0;
   const bool shuffle = mode != nullptr && std::strncmp(mode, "shuffle", 7) == 0;
   unsigned long long rng = 0x9E3779B97F4A7C15ull ^ (shuffle && mode[7] == ':' ? std::strtoull(mode + 8, nullptr, 10) : 0ull) ^
-                           ((unsigned long long)bid << 32);
-  std::vector<int> order(nthreads);
-  for (int t = 0; t < nthreads; ++t) order[t] = reverse ? nthreads - 1 - t : t;
+                           ((unsigned long long)bid0 << 32);
+  std::vector<int> order(nfib);
+  for (int t = 0; t < nfib; ++t) order[t] = reverse ? nfib - 1 - t : t;
   bool alive = true;
   while (alive) {
     alive = false;
     if (shuffle)
-      for (int t = nthreads - 1; t > 0; --t) {
+      for (int t = nfib - 1; t > 0; --t) {
         rng = rng * 6364136223846793005ull + 1442695040888963407ull;
         const int r = (int)((rng >> 33) % (unsigned long long)(t + 1));
         const int tmp = order[t];
         order[t] = order[r];
         order[r] = tmp;
       }
-    for (int k = 0; k < nthreads; ++k) {
+    for (int k = 0; k < nfib; ++k) {
       const int t = order[k];
       if (s.done[t]) continue;
-      cta.cur = t;
+      g_cta = &ctas[t / nthreads];
+      g_cta->cur = t % nthreads;
       swapcontext(&s.main_ctx, &s.ctx[t]);
       if (!s.done[t]) alive = true;
     }
   }
-  for (int t = 0; t < nthreads; ++t) std::free(s.stacks[t]);
+  for (int t = 0; t < nfib; ++t) std::free(s.stacks[t]);
   g_cta = nullptr;
   g_sched = nullptr;
 }
 
-// run a grid, CTAs spread over host threads
-inline void run_grid(int grid, int nthreads, size_t smem_doubles, void (*body)(void*), void* arg, int host_threads) {
+// run a grid (of clusters of `csize` CTAs; grid is rounded down to whole clusters), clusters spread over host threads
+inline void run_grid(int grid, int nthreads, size_t smem_doubles, void (*body)(void*), void* arg, int host_threads, int csize = 1) {
+  const int ncl = grid / csize > 0 ? grid / csize : 1;
+  grid = ncl * csize;
   if (host_threads < 1) host_threads = 1;
-  if (host_threads > grid) host_threads = grid;
+  if (host_threads > ncl) host_threads = ncl;
   std::vector<std::thread> pool;
   for (int w = 0; w < host_threads; ++w)
     pool.emplace_back([=]() {
-      for (int b = w; b < grid; b += host_threads) run_cta(nthreads, b, grid, smem_doubles, body, arg);
+      for (int b = w; b < ncl; b += host_threads) run_cluster(csize, nthreads, b * csize, grid, smem_doubles, body, arg);
     });
   for (auto& th : pool) th.join();
 }
