@@ -18,10 +18,11 @@
 //   * s_Kh [4][9][NM^2]   the blocks K~_{k,k+d}, d_z = 1, of the plane BELOW the slab (owned by the lower neighbour;
 //                         assembled redundantly here so that no matrix entry is ever read through DSMEM);
 //   * s_p  [(PZ+2) NM^2][18]  search directions of all 6 right-hand sides, node-major, own planes + one HALO plane
-//                         below and above.  After every update the owners of the two boundary planes store their
-//                         values straight into the neighbour CTAs' halo planes (st through a mapa address = DSMEM),
-//                         then barrier.cluster.arrive; the part of y = K p that needs no halo runs before
-//                         barrier.cluster.wait, so the SM-to-SM transfer is hidden behind it.
+//                         below and above.  After every update one thread hands the two boundary planes (9 KB each,
+//                         contiguous) to the copy engine: cp.async.bulk shared::cta -> shared::cluster into the
+//                         neighbours' halo planes, completion counted as transaction bytes on the RECEIVER's mbarrier.
+//                         The part of y = K p that needs no halo runs first, the four (of 14) block products per
+//                         boundary node that do wait on that mbarrier: the SM-to-SM transfer hides behind the rest.
 // Threads: TPN = 2 threads per node (lanes 2j, 2j+1 of a warp), each owning 3 of the 6 right-hand sides: its x~, r~
 // (and y = K p while it is formed) live in REGISTERS; a matrix block is loaded once per thread pair and row (the
 // two lanes read the same address: one shared-memory wavefront) and used for 27 FMA per thread.  The apply is a pure
@@ -34,8 +35,8 @@
 //
 // Cluster-wide reductions (p.Kp; r~.r~ together with the restricted residual P^T r): warp shuffles -> CTA partial
 // -> every CTA stores its partial into every CTA's receive buffer (DSMEM) -> barrier.cluster -> every CTA adds the
-// partials in rank order: all CTAs hold bit-identical scalars and take identical branches.  Three cluster barriers per
-// iteration.  r.z needs no second reduction: r~.z~ = r~.r~ + (P^T r).E^-1 (P^T r).
+// partials in rank order: all CTAs hold bit-identical scalars and take identical branches.  Two cluster barriers per
+// iteration (they also order the reuse of the halo planes and receive buffers).  r.z needs no second reduction: r~.z~ = r~.r~ + (P^T r).E^-1 (P^T r).
 // Coarse space: the semi-coarsened space of hmx_cell_coarse.cuh (level-1 Kuhn P1 summed along the first micro axis
 // when the coefficient does not depend on it), set up by the same coarse_setup in every CTA; restriction = line sums
 // along x (warp shuffles) followed by the 2-D Kuhn restriction of the lines a CTA owns.
@@ -69,7 +70,9 @@ struct ClusterLayout {
   using CS = CoarseSpace<CO, NM, NT, 0, 0, 0>;
   // two-level preconditioner: the semi-coarsened space along axis 0 (the z-slabs must not cut the summed axis and the
   // line sums run along the lanes of a warp)
-  static constexpr bool TWO = CS::GEOM && CS::SEMI && CS::SA == 0 && CS::NCD <= CS::MAXDOF;
+  // ... and the scratch of coarse_setup fits in the matrix area of one CTA (8^3 yes, 10^3 no: block Jacobi then)
+  static constexpr bool TWO = CS::GEOM && CS::SEMI && CS::SA == 0 && CS::NCD <= CS::MAXDOF &&
+                              CS::setup_doubles <= ((1 << D) - 1) * D * D * (NM / CL) * NM * NM + 4 * D * D * NM * NM;
   static constexpr int NCD = TWO ? CS::NCD : 2;
   static constexpr int NTRI = TWO ? CS::NTRI : 0;
   static constexpr int NC2 = TWO ? CS::NC2 : 1;
@@ -82,7 +85,8 @@ struct ClusterLayout {
   static constexpr int EPART = NT / (NRHS * NRHS);  // node partitions of the epilogue's cross products
   HMX_HOSTDEV static constexpr int imax(int a, int b) { return a > b ? a : b; }
   // ---- shared memory (doubles) ----
-  static constexpr int o_red = 0;                                    // [NW][8] warp partials
+  static constexpr int o_bar = 0;                                    // mbarrier of the halo planes (HMX_MBAR_BYTES)
+  static constexpr int o_red = o_bar + HMX_MBAR_BYTES / 8;           // [NW][8] warp partials
   static constexpr int o_xch = o_red + NW * 8;                       // [CL][8] p.Kp partials of every CTA
   static constexpr int o_recv = o_xch + CL * 8;                      // [CL][NREC] restricted residual + r~.r~ partials
   static constexpr int o_scal = o_recv + CL * NREC;                  // [8] r~.r~ of every right-hand side
@@ -98,12 +102,19 @@ struct ClusterLayout {
   static constexpr int total = o_Kh + 4 * NB * NPL;
   // set-up aliases: atoms [NA1][T][NRC] and the inverse Cholesky factors [6][NPB] live in the p area, the scratch
   // of coarse_setup in the matrix area (both dead before the first search direction / matrix block is written)
+  // (coefficients with many atoms on all three axes: the atoms go to this CTA's global scratch instead -- set-up only)
+  static constexpr bool ATG = NA1 * T * NRC + 6 * NPB + 6 * NOWN > NPB * NVEC;
   static constexpr int o_atoms = o_p;
-  static constexpr int o_li = o_p + NA1 * T * NRC;
-  static_assert(NA1 * T * NRC + 6 * NPB <= NPB * NVEC, "atoms + inverse factors must fit in the p area during set-up");
+  static constexpr int o_li = o_p + (ATG ? 0 : NA1 * T * NRC);  // [6][NPB] inverse factors (own + halo planes)
+  static constexpr int o_lf = o_li + 6 * NPB;                   // [6][NOWN] factors of the own nodes
+  static_assert(6 * NPB + 6 * NOWN <= NPB * NVEC, "Cholesky factors must fit in the p area during set-up");
+  // diagonal-block partials of the two halves of the simplex types, [2][27][NOWN] own + [2][9][2 NPL] halo: matrix area
+  static_assert(2 * 27 * NOWN + 2 * 9 * 2 * NPL <= NH * NB * NOWN + 4 * NB * NPL, "diagonal partials must fit in the matrix area");
+  static constexpr int PLANE_BYTES = NPL * NVEC * 8;
+  static_assert(PLANE_BYTES % 16 == 0 && (o_p * 8) % 16 == 0 && HMX_MBAR_BYTES % 8 == 0, "bulk copies of whole node planes");
   static_assert(!TWO || CS::setup_doubles <= NH * NB * NOWN + 4 * NB * NPL, "coarse set-up scratch must fit in the matrix area");
   static_assert(2 * NOWN * NVEC <= NH * NB * NOWN + 4 * NB * NPL, "epilogue copies of r~ and b~ must fit in the matrix area");
-  static constexpr int scratch_doubles = NOWN * NVEC;  // b~ of the own nodes, per CTA
+  static constexpr int scratch_doubles = NOWN * NVEC + (ATG ? NA1 * T * NRC : 0);  // b~ of the own nodes (+ atoms), per CTA
   static_assert(NM % CL == 0, "the cluster splits the cell into slabs of whole node planes");
   static_assert(TPN >= 1 && TPN <= 2 && NRHS % TPN == 0 && NT % 32 == 0 && NT >= NOWN * TPN && 32 % TPN == 0, "TPN threads per own node");
   static_assert(NT >= NRHS * NCD + NRHS && NT >= NRHS * NRHS, "one thread per coarse unknown and right-hand side in the exchanges");
@@ -124,49 +135,51 @@ HMX_DEV void cl_basis_strain(const double (&m)[3], int j, double (&e)[6]) {
     }
 }
 
-// Block K_{i, i+dir} of the periodic stiffness matrix for the node with (global, periodic) coordinates c:
-// dir = 0 the diagonal block, dir = 1..7 the positive Kuhn direction with that bit mask.  blk[r * 3 + s] couples
-// component r at node i with component s at node i + dir.  With RHS the load vectors of all right-hand sides ride
-// along with the diagonal block: rhs[q * 3 + j] = b_q[i][j] = -|e| sum_elements (C E_q) : e(phi_i e_j)  (hmm.py:898-903).
-template <class CO, int NM, bool RHS>
-HMX_DEV void cl_block(const int (&c)[3], int dir, const double* pc, const double (&Mn)[9], const double* s_atoms, double vol,
-                      double (&blk)[9], double (&rhs)[18]) {
+// vertex b >= a of a type-t simplex with P(t, b) - P(t, a) = dir (dir = 0: b = a), or -1
+HMX_HOSTDEV constexpr int cl_bsel(int t, int a, int dir) {
+  int r = -1;
+  for (int b = a; b <= 3; ++b)
+    if ((kuhn_pmask<3>(t, b) & ~kuhn_pmask<3>(t, a)) == dir) r = b;
+  return r;
+}
+
+// blk += the contributions of the simplex types 3 PART .. 3 PART + 2 to the block K_{i, i+DIR} of the periodic stiffness
+// matrix, i = the node with (global, periodic) coordinates c:  DIR = 0 the diagonal block, DIR = 1..7 the positive Kuhn
+// direction with that bit mask.  blk[r * 3 + s] couples component r at node i with component s at node i + DIR.
+// With RHS the load vectors of all right-hand sides ride along with the diagonal block:
+//   rhs[q * 3 + j] += their share of  b_q[i][j] = -|e| sum_elements (C E_q) : e(phi_i e_j)   (hmm.py:898-903).
+// Everything about the mesh is folded at compile time (types, vertices, directions); one copy of the code per
+// (DIR, PART), called from the own-node and the halo-node loops.
+template <class CO, int NM, int DIR, int PART, bool RHS>
+HMX_DEV_NOINLINE void cl_block(const int* c_in, const double* pc, const double* Mn, const double* s_atoms, double vol, double* blk,
+                               double* rhs) {
   using G = Grid<3, NM, 0>;
   using AI = AtomIdx<3, NM, CO::YDEP, true>;
   constexpr int D = 3, T = 6, NV = 6, NA = CO::NATOMS, NA1 = NA > 0 ? NA : 1, NRC = AI::NRC;
+  const int c[3] = {c_in[0], c_in[1], c_in[2]};
   HMX_UNROLL
-  for (int k = 0; k < 9; ++k) blk[k] = 0.0;
-#ifndef HMX_EMULATE
-#pragma unroll 1
-#endif
-  for (int t = 0; t < T; ++t) {
-    // M-transformed gradients of the four vertex functions of a type-t simplex
-    double g[D + 1][D];
-    for (int a = 0; a <= D; ++a)
-      HMX_UNROLL
-      for (int p = 0; p < D; ++p) {
-        g[a][p] = 0.0;
-        if (a >= 1) g[a][p] += Mn[p * D + kuhn_axis<D>(t, a - 1 >= 0 ? a - 1 : 0)];
-        if (a < D) g[a][p] -= Mn[p * D + kuhn_axis<D>(t, a < D ? a : 0)];
-      }
+  for (int tt = 0; tt < 3; ++tt) {
+    const int t = 3 * PART + tt;
+    HMX_UNROLL
     for (int a = 0; a <= D; ++a) {
-      // the type-t simplex in which node i is vertex a: does it have an edge a -> b, b >= a, in direction dir ?
-      const int ma = kuhn_pmask<D>(t, a);
-      int bsel = -1;
-      for (int b = a; b <= D; ++b)
-        if ((kuhn_pmask<D>(t, b) & ~ma) == dir) bsel = b;  // (b = a gives 0: the diagonal)
-      if (bsel < 0) continue;
+      // the type-t simplex in which node i is vertex a: its edge a -> b in direction DIR, if it has one
+      const int b = cl_bsel(t, a, DIR);
+      if (b < 0) continue;
       int o[3];
-      G::template shift_coords<-1>(c, ma, o);
+      G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
       const int ro = AI::ridx(o);
       double sa[NA1];
       HMX_UNROLL
       for (int k = 0; k < NA1; ++k) sa[k] = NA > 0 ? s_atoms[(k * T + t) * NRC + ro] : 0.0;
-      double ga[D], gb[D];
+      double ga[D], gb[D];  // M-transformed gradients of the vertex functions a and b
       HMX_UNROLL
       for (int p = 0; p < D; ++p) {
-        ga[p] = g[a][p];
-        gb[p] = g[bsel][p];
+        ga[p] = 0.0;
+        if (a >= 1) ga[p] += Mn[p * D + kuhn_axis<D>(t, a >= 1 ? a - 1 : 0)];
+        if (a < D) ga[p] -= Mn[p * D + kuhn_axis<D>(t, a < D ? a : 0)];
+        gb[p] = 0.0;
+        if (b >= 1) gb[p] += Mn[p * D + kuhn_axis<D>(t, b >= 1 ? b - 1 : 0)];
+        if (b < D) gb[p] -= Mn[p * D + kuhn_axis<D>(t, b < D ? b : 0)];
       }
       double eb[D][NV];
       HMX_UNROLL
@@ -228,6 +241,7 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
 
   double* sm = dyn_smem();
+  MBar* s_bar = reinterpret_cast<MBar*>(sm + L::o_bar);
   double* s_red = sm + L::o_red;
   double* s_xch = sm + L::o_xch;
   double* s_recv = sm + L::o_recv;
@@ -238,9 +252,10 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   double* s_p = sm + L::o_p;
   double* s_K = sm + L::o_K;
   double* s_Kh = sm + L::o_Kh;
-  double* s_atoms = sm + L::o_atoms;
-  double* s_li = sm + L::o_li;  // [6][NPB] inverse Cholesky factors of the diagonal blocks (set-up only)
   double* g_b = P.scratch + (size_t)bid() * L::scratch_doubles;
+  double* s_atoms = L::ATG ? g_b + NOWN * NVEC : sm + L::o_atoms;
+  double* s_li = sm + L::o_li;  // [6][NPB] inverse Cholesky factors of the diagonal blocks (set-up only)
+  double* s_lf = sm + L::o_lf;  // [6][NOWN] Cholesky factors of the own nodes (set-up only)
 
   const int t_id = tid(), lane = t_id & 31, warp = t_id >> 5;
   const int rank = cluster_rank();
@@ -254,15 +269,20 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   const int oyp = cy + 1 < NM ? NM : NM - NPL, oym = cy > 0 ? -NM : NPL - NM;
   const int pb = j + NPL;  // own slot in the p buffer
   const int r_lo = (rank + CL - 1) % CL, r_up = (rank + 1) % CL;
-  double* p_lo = cluster_map(s_p, r_lo);  // the lower / upper neighbour's p buffer (DSMEM)
-  double* p_up = cluster_map(s_p, r_up);
   const double hh = 1.0 / (double)NM;
   const double vol = hh * hh * hh / 6.0;
   const double sqrtw = sqrt(vol);
   int red_flip = 0;
+  unsigned halo_parity = 0;
   // offset of direction mask m (bits x, y, z) from node slot s of the p buffer, forwards / backwards
   auto fwd = [&](int m) { return ((m & 1) ? oxp : 0) + ((m & 2) ? oyp : 0) + ((m & 4) ? NPL : 0); };
   auto bwd = [&](int m) { return ((m & 1) ? oxm : 0) + ((m & 2) ? oym : 0) - ((m & 4) ? NPL : 0); };
+
+  if (t_id == 0) {
+    mbar_init(s_bar, 1);
+    mbar_fence_init();
+  }
+  cluster_sync();  // every CTA's mbarrier exists before a peer's copy can signal it
 
   for (long long pt = cluster_id(); pt < P.n_pts; pt += nclusters()) {
     double xm[3], verts[(D + 1) * 3];
@@ -317,49 +337,92 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
     // ---- 2. coarse matrix of this point, inverted (scratch: the matrix area) ----
     if constexpr (TWO) coarse_setup<CS, CO, NM, NT>(pc, Ms, s_atoms, s_K, s_ei, s_work, s_red, NW * 8 / 2, red_flip);
 
-    // ---- 3. diagonal blocks -> Cholesky factors, load vectors ----
-    double Lf[6], Li[6], bt[NVL];
+    // ---- 3. diagonal blocks: the two halves of the simplex types in parallel (warp-uniform when NOWN is a multiple
+    //         of 32), partial sums through the matrix area ----
     {
-      double blk[9], rhs[18];
-      HMX_UNROLL
-      for (int k = 0; k < 18; ++k) rhs[k] = 0.0;
-      const int c[3] = {cx, cy, zg};
-      cl_block<CO, NM, true>(c, 0, pc, Mn, s_atoms, vol, blk, rhs);
-      cl_chol3(blk, Lf, Li);
-      if (own && h == 0) {
+      double* s_dp = s_K;                    // [2][27][NOWN] partial diagonal blocks + load vectors of the own nodes
+      double* s_dh = s_K + 2 * 27 * NOWN;    // [2][9][2 NPL] partial diagonal blocks of the two halo planes
+      for (int task = t_id; task < 2 * (NOWN + 2 * NPL); task += NT) {
+        const bool halo = task >= 2 * NOWN;
+        const int u = halo ? task - 2 * NOWN : task, cnt = halo ? 2 * NPL : NOWN;
+        const int part = u / cnt, k = u - part * cnt;
+        int c[3];
+        if (halo) {
+          const int up = k / NPL, kk = k - up * NPL;
+          c[0] = kk % NM;
+          c[1] = kk / NM;
+          c[2] = (rank * PZ + (up ? PZ : NM - 1)) % NM;
+        } else {
+          c[0] = k % NM;
+          c[1] = (k / NM) % NM;
+          c[2] = rank * PZ + k / NPL;
+        }
+        double blk[9], rhs[18];
         HMX_UNROLL
-        for (int k = 0; k < 6; ++k) s_li[k * NPB + pb] = Li[k];
-      }
-      // b~ = L^-1 b for this thread's right-hand sides
-      HMX_UNROLL
-      for (int q = 0; q < NRL; ++q) {
-        const int qg = h * NRL + q;
+        for (int e = 0; e < 9; ++e) blk[e] = 0.0;
         HMX_UNROLL
-        for (int r = 0; r < D; ++r) {
-          double v = 0.0;
+        for (int e = 0; e < 18; ++e) rhs[e] = 0.0;
+        if (halo) {
+          if (part == 0)
+            cl_block<CO, NM, 0, 0, false>(c, pc, Mn, s_atoms, vol, blk, rhs);
+          else
+            cl_block<CO, NM, 0, 1, false>(c, pc, Mn, s_atoms, vol, blk, rhs);
           HMX_UNROLL
-          for (int s = 0; s <= r; ++s) v += Li[cl_tri(r, s)] * rhs[qg * D + s];
-          bt[q * D + r] = v;
+          for (int e = 0; e < 9; ++e) s_dh[(part * 9 + e) * 2 * NPL + k] = blk[e];
+        } else {
+          if (part == 0)
+            cl_block<CO, NM, 0, 0, true>(c, pc, Mn, s_atoms, vol, blk, rhs);
+          else
+            cl_block<CO, NM, 0, 1, true>(c, pc, Mn, s_atoms, vol, blk, rhs);
+          HMX_UNROLL
+          for (int e = 0; e < 9; ++e) s_dp[(part * 27 + e) * NOWN + k] = blk[e];
+          HMX_UNROLL
+          for (int e = 0; e < 18; ++e) s_dp[(part * 27 + 9 + e) * NOWN + k] = rhs[e];
         }
       }
+      sync();
+      // Cholesky factors; b~ = L^-1 b of every right-hand side -> scratch
+      for (int task = t_id; task < NOWN + 2 * NPL; task += NT) {
+        const bool halo = task >= NOWN;
+        const int k = halo ? task - NOWN : task;
+        double blk[9], lf[6], li[6];
+        HMX_UNROLL
+        for (int e = 0; e < 9; ++e)
+          blk[e] = halo ? s_dh[e * 2 * NPL + k] + s_dh[(9 + e) * 2 * NPL + k] : s_dp[e * NOWN + k] + s_dp[(27 + e) * NOWN + k];
+        cl_chol3(blk, lf, li);
+        const int slot = halo ? (k < NPL ? k : (PZ + 1) * NPL + (k - NPL)) : NPL + k;
+        HMX_UNROLL
+        for (int e = 0; e < 6; ++e) s_li[e * NPB + slot] = li[e];
+        if (!halo) {
+          HMX_UNROLL
+          for (int e = 0; e < 6; ++e) s_lf[e * NOWN + k] = lf[e];
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) {
+            double b[D];
+            HMX_UNROLL
+            for (int r = 0; r < D; ++r) b[r] = s_dp[(9 + q * D + r) * NOWN + k] + s_dp[(27 + 9 + q * D + r) * NOWN + k];
+            HMX_UNROLL
+            for (int r = 0; r < D; ++r) {
+              double v = 0.0;
+              HMX_UNROLL
+              for (int s = 0; s <= r; ++s) v += li[cl_tri(r, s)] * b[s];
+              g_b[(size_t)k * NVEC + q * D + r] = v;
+            }
+          }
+        }
+      }
+      sync();
     }
-    // the two halo planes (the nodes of the neighbouring slabs this slab's blocks couple to)
-    for (int idx = t_id; idx < 2 * NPL; idx += NT) {
-      const int up = idx / NPL, k = idx - up * NPL;
-      const int c[3] = {k % NM, k / NM, (rank * PZ + (up ? PZ : NM - 1)) % NM};
-      double blk[9], rhs[18], lf[6], li[6];
-      cl_block<CO, NM, false>(c, 0, pc, Mn, s_atoms, vol, blk, rhs);
-      cl_chol3(blk, lf, li);
-      HMX_UNROLL
-      for (int e = 0; e < 6; ++e) s_li[e * NPB + (up ? (PZ + 1) * NPL : 0) + k] = li[e];
-    }
-    sync();
 
     // ---- 4. scaled off-diagonal blocks  K~_{i,i+d} = L_i^-1 K_{i,i+d} L_{i+d}^-T ----
-    auto scale_store = [&](const double (&blk)[9], const double (&li)[6], int nb_slot, double* dst, int stride) {
-      double lj[6];
+    // dst[(r * 3 + s) * stride] (=|+=) the scaled block
+    auto scale_store = [&](const double (&blk)[9], int slot, int nb_slot, double* dst, int stride, bool add) {
+      double li[6], lj[6];
       HMX_UNROLL
-      for (int e = 0; e < 6; ++e) lj[e] = s_li[e * NPB + nb_slot];
+      for (int e = 0; e < 6; ++e) {
+        li[e] = s_li[e * NPB + slot];
+        lj[e] = s_li[e * NPB + nb_slot];
+      }
       double t1[9];
       HMX_UNROLL
       for (int r = 0; r < D; ++r)
@@ -377,37 +440,82 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
           double v = 0.0;
           HMX_UNROLL
           for (int k = 0; k <= s; ++k) v += t1[r * D + k] * lj[cl_tri(s, k)];
-          dst[(r * D + s) * stride] = v;
+          if (add)
+            dst[(r * D + s) * stride] += v;
+          else
+            dst[(r * D + s) * stride] = v;
         }
     };
-    if (own) {
-      const int c[3] = {cx, cy, zg};
-      for (int d = 1 + h; d <= NH; d += TPN) {
-        double blk[9], rhs[18];
-        cl_block<CO, NM, false>(c, d, pc, Mn, s_atoms, vol, blk, rhs);
-        scale_store(blk, Li, pb + fwd(d), s_K + (size_t)(d - 1) * NB * NOWN + j, NOWN);
+    {
+      // own nodes: thread (node k, half `part` of the simplex types); part 0 stores, part 1 adds after a barrier
+      constexpr bool PAR = NT >= 2 * NOWN;
+      const int part = PAR ? t_id / NOWN : 0, k = PAR ? t_id - part * NOWN : t_id;
+      const bool on = PAR ? part < 2 : k < NOWN;
+      const int kx = k % NM, ky = (k / NM) % NM, kz = k / NPL;
+      const int c[3] = {kx, ky, rank * PZ + kz};
+      double rhs[1] = {0.0};
+      auto block_dir = [&](auto dtag) {
+        constexpr int DIR = decltype(dtag)::value;
+        double blk[9];
+        HMX_UNROLL
+        for (int e = 0; e < 9; ++e) blk[e] = 0.0;
+        if (on) {
+          if (!PAR || part == 0) cl_block<CO, NM, DIR, 0, false>(c, pc, Mn, s_atoms, vol, blk, rhs);
+          if (!PAR || part == 1) cl_block<CO, NM, DIR, 1, false>(c, pc, Mn, s_atoms, vol, blk, rhs);
+        }
+        const int nb = NPL + ((DIR & 1) ? (kx + 1) % NM : kx) + NM * ((DIR & 2) ? (ky + 1) % NM : ky) + NPL * (kz + ((DIR & 4) ? 1 : 0));
+        double* dst = s_K + (size_t)(DIR - 1) * NB * NOWN + k;
+        if (on && part == 0) scale_store(blk, NPL + k, nb, dst, NOWN, false);
+        if (PAR) {
+          sync();
+          if (on && part == 1) scale_store(blk, NPL + k, nb, dst, NOWN, true);
+        }
+      };
+      block_dir(IntTag<1>{});
+      block_dir(IntTag<2>{});
+      block_dir(IntTag<3>{});
+      block_dir(IntTag<4>{});
+      block_dir(IntTag<5>{});
+      block_dir(IntTag<6>{});
+      block_dir(IntTag<7>{});
+      // the plane below: its blocks towards this slab (directions with a z step)
+      for (int idx = t_id; idx < 4 * NPL; idx += NT) {
+        const int dd = idx / NPL, kk = idx - dd * NPL;
+        const int hx = kk % NM, hy = kk / NM;
+        const int ch[3] = {hx, hy, (rank * PZ + NM - 1) % NM};
+        double blk[9];
+        HMX_UNROLL
+        for (int e = 0; e < 9; ++e) blk[e] = 0.0;
+        if (dd == 0) {
+          cl_block<CO, NM, 4, 0, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+          cl_block<CO, NM, 4, 1, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+        } else if (dd == 1) {
+          cl_block<CO, NM, 5, 0, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+          cl_block<CO, NM, 5, 1, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+        } else if (dd == 2) {
+          cl_block<CO, NM, 6, 0, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+          cl_block<CO, NM, 6, 1, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+        } else {
+          cl_block<CO, NM, 7, 0, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+          cl_block<CO, NM, 7, 1, false>(ch, pc, Mn, s_atoms, vol, blk, rhs);
+        }
+        const int d = 4 + dd;
+        const int nb = NPL + ((d & 1) ? (hx + 1) % NM : hx) + NM * ((d & 2) ? (hy + 1) % NM : hy);
+        scale_store(blk, kk, nb, s_Kh + (size_t)dd * NB * NPL + kk, NPL, false);
       }
     }
-    for (int idx = t_id; idx < 4 * NPL; idx += NT) {  // the plane below: its blocks towards this slab
-      const int dd = idx / NPL, k = idx - dd * NPL, d = 4 + dd;
-      const int kx = k % NM, ky = k / NM;
-      const int c[3] = {kx, ky, (rank * PZ + NM - 1) % NM};
-      double blk[9], rhs[18], li[6];
-      cl_block<CO, NM, false>(c, d, pc, Mn, s_atoms, vol, blk, rhs);
-      HMX_UNROLL
-      for (int e = 0; e < 6; ++e) li[e] = s_li[e * NPB + k];
-      const int nb = NPL + ((d & 1) ? (kx + 1) % NM : kx) + NM * ((d & 2) ? (ky + 1) % NM : ky);
-      scale_store(blk, li, nb, s_Kh + (size_t)dd * NB * NPL + k, NPL);
-    }
-    sync();  // the matrix is complete; atoms and inverse factors (p area) are dead
+    // this thread's Cholesky factor and load vectors
+    double Lf[6];
+    HMX_UNROLL
+    for (int e = 0; e < 6; ++e) Lf[e] = s_lf[e * NOWN + j];
+    sync();  // the matrix is complete; atoms and factors (p area) are dead
 
     // ---- 5. PCG on the scaled system, all right-hand sides in lock step ----
     double xt[NVL], rt[NVL];
     HMX_UNROLL
     for (int k = 0; k < NVL; ++k) {
       xt[k] = 0.0;
-      rt[k] = own ? bt[k] : 0.0;
-      if (own) g_b[(size_t)j * NVEC + h * NVL + k] = bt[k];
+      rt[k] = own ? g_b[(size_t)j * NVEC + h * NVL + k] : 0.0;
     }
     // sum of one value per right-hand side of this thread over the CTA -> s_red[warp][h * NRL + q]
     auto warp_partials = [&](const double (&v)[NRL]) {
@@ -552,66 +660,49 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
         }
       }
     };
-    // publish this thread's search direction: own slot and, from the boundary planes, the neighbours' halo planes
-    auto publish = [&](const double (&pv)[NVL]) {
-      if (own) {
-        HMX_UNROLL
-        for (int k = 0; k < NVL; ++k) s_p[(size_t)pb * NVEC + h * NVL + k] = pv[k];
-        if (zl == 0) {
-          HMX_UNROLL
-          for (int k = 0; k < NVL; ++k) p_lo[(size_t)((PZ + 1) * NPL + cx + NM * cy) * NVEC + h * NVL + k] = pv[k];
-        }
-        if (zl == PZ - 1) {
-          HMX_UNROLL
-          for (int k = 0; k < NVL; ++k) p_up[(size_t)(cx + NM * cy) * NVEC + h * NVL + k] = pv[k];
-        }
-      }
-    };
 
-    double pv[NVL], rz[NRL];
+    // the search direction of this thread lives in its own slot of s_p only (no register copy: the slot is rewritten
+    // after the two cluster barriers that follow the products reading it)
+    double* p_own = s_p + (size_t)pb * NVEC + h * NVL;
+    double rz[NRL], tol2[NRL];
     bool active[NRL];
     int it[NRL];
+    double rz0[NRL];
     {
       double z[NVL];
       precond(rt, z, rz);
       HMX_UNROLL
-      for (int k = 0; k < NVL; ++k) pv[k] = z[k];
-    }
-    HMX_UNROLL
-    for (int q = 0; q < NRL; ++q) {
-      active[q] = rz[q] > P.atol * P.atol;
-      it[q] = 0;
-      if (!active[q]) {
+      for (int q = 0; q < NRL; ++q) {
+        rz0[q] = rz[q];
+        active[q] = rz0[q] > P.atol * P.atol;
+        tol2[q] = fmax(P.rtol * P.rtol * rz0[q], P.atol * P.atol);
+        it[q] = 0;
         HMX_UNROLL
-        for (int c = 0; c < D; ++c) pv[q * D + c] = 0.0;
+        for (int c = 0; c < D; ++c)
+          if (own) p_own[q * D + c] = active[q] ? z[q * D + c] : 0.0;
       }
     }
     int iter = 0;
-    // r~.z~ and the convergence flags of ALL right-hand sides: the loop condition must be uniform over the cluster,
-    // and every thread reads the cluster-wide scalars anyway (the same sums in the same order as `rz` above)
-    double rz_all[NRHS], rz0_all[NRHS];
-    bool act_all[NRHS];
-    HMX_UNROLL
-    for (int q = 0; q < NRHS; ++q) {
-      double s = s_scal[q];
-      if (TWO)
-        for (int rb = 0; rb < NBLK; ++rb) s += s_work[NRHS * NCD + q * NBLK + rb];
-      rz_all[q] = rz0_all[q] = s;
-      act_all[q] = s > P.atol * P.atol;
-    }
-    publish(pv);
     while (true) {
-      bool go = false;
+      // uniform over the cluster: r~.z~ comes from cluster-wide scalars that are bit-identical in every thread with the
+      // same half, and every warp holds both halves
+      bool mine = false;
       HMX_UNROLL
-      for (int q = 0; q < NRHS; ++q) go = go || act_all[q];
-      if (!go || iter >= P.max_it) break;
+      for (int q = 0; q < NRL; ++q) mine = mine || active[q];
+      if (!warp_any(mine) || iter >= P.max_it) break;
       ++iter;
-      cluster_arrive();  // releases p (own slots and the halo planes written into the neighbours)
-      sync();            // this CTA's own p is complete
-      // ---- y = K~ p: identity diagonal + 14 off-diagonal blocks; visits that read a halo plane wait for the cluster ----
+      // the search directions are in place (own slots): hand the two boundary planes to the neighbours' halo planes
+      sync();
+      if (t_id == 0) {
+        fence_async_proxy();  // the planes were written through the generic proxy
+        mbar_arrive_expect_tx(s_bar, 2 * L::PLANE_BYTES);
+        bulk_s2c(s_p + (size_t)(PZ + 1) * NPL * NVEC, s_p + (size_t)NPL * NVEC, L::PLANE_BYTES, s_bar, r_lo);
+        bulk_s2c(s_p, s_p + (size_t)PZ * NPL * NVEC, L::PLANE_BYTES, s_bar, r_up);
+      }
+      // ---- y = K~ p: identity diagonal + 14 off-diagonal blocks; the products that read a halo plane come last ----
       double y[NVL];
       HMX_UNROLL
-      for (int k = 0; k < NVL; ++k) y[k] = pv[k];
+      for (int k = 0; k < NVL; ++k) y[k] = p_own[k];
       auto visit_fwd = [&](int d) {  // y_i += K~_{i,i+d} p_{i+d}
         const double* kb = s_K + (size_t)(d - 1) * NB * NOWN + j;
         const double* pn = s_p + (size_t)(pb + fwd(d)) * NVEC + h * NVL;
@@ -651,7 +742,8 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
         if (!((d & 4) && top)) visit_fwd(d);
         if (!((d & 4) && bot)) visit_bwd(d);
       }
-      cluster_wait();  // the neighbours' boundary planes have arrived in the halo planes
+      mbar_wait(s_bar, halo_parity);  // the neighbours' boundary planes have landed in the halo planes
+      halo_parity ^= 1u;
       HMX_UNROLL
       for (int d = 4; d <= NH; ++d) {
         if (top) visit_fwd(d);
@@ -664,7 +756,7 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
         for (int q = 0; q < NRL; ++q) {
           part[q] = 0.0;
           HMX_UNROLL
-          for (int c = 0; c < D; ++c) part[q] += own ? pv[q * D + c] * y[q * D + c] : 0.0;
+          for (int c = 0; c < D; ++c) part[q] += own ? p_own[q * D + c] * y[q * D + c] : 0.0;
         }
         warp_partials(part);
         sync();
@@ -676,56 +768,36 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
         }
         cluster_sync();
       }
-      double alpha_all[NRHS];
-      HMX_UNROLL
-      for (int q = 0; q < NRHS; ++q) {
-        double pAp = 0.0;
-        for (int rk = 0; rk < CL; ++rk) pAp += s_xch[rk * 8 + q];
-        alpha_all[q] = (act_all[q] && pAp > 0.0) ? fast_div(rz_all[q], pAp) : 0.0;
-      }
       HMX_UNROLL
       for (int q = 0; q < NRL; ++q) {
-        const double alpha = h == 0 ? alpha_all[q] : alpha_all[(TPN - 1) * NRL + q];
+        double pAp = 0.0;
+        for (int rk = 0; rk < CL; ++rk) pAp += s_xch[rk * 8 + h * NRL + q];
+        const double alpha = (active[q] && pAp > 0.0) ? fast_div(rz[q], pAp) : 0.0;
         if (active[q]) ++it[q];
         HMX_UNROLL
         for (int c = 0; c < D; ++c) {
-          xt[q * D + c] = own ? fma(alpha, pv[q * D + c], xt[q * D + c]) : 0.0;  // (idle threads keep zeros)
+          xt[q * D + c] = own ? fma(alpha, p_own[q * D + c], xt[q * D + c]) : 0.0;  // (idle threads keep zeros)
           rt[q * D + c] = own ? fma(-alpha, y[q * D + c], rt[q * D + c]) : 0.0;
         }
       }
       double z[NVL], rzn[NRL];
       precond(rt, z, rzn);
-      // new r~.z~ of every right-hand side (both halves read the same shared scalars)
-      HMX_UNROLL
-      for (int q = 0; q < NRHS; ++q) {
-        double s = s_scal[q];
-        if (TWO)
-          for (int rb = 0; rb < NBLK; ++rb) s += s_work[NRHS * NCD + q * NBLK + rb];
-        if (act_all[q]) {
-          const double beta = fast_div(s, rz_all[q]);
-          rz_all[q] = s;
-          const bool still = s > fmax(P.rtol * P.rtol * rz0_all[q], P.atol * P.atol);
-          act_all[q] = still;
-          alpha_all[q] = still ? beta : -1.0;  // (reused as beta; -1 marks "just converged")
-        } else {
-          alpha_all[q] = -1.0;
-        }
-      }
       HMX_UNROLL
       for (int q = 0; q < NRL; ++q) {
-        const double beta = h == 0 ? alpha_all[q] : alpha_all[(TPN - 1) * NRL + q];
-        const bool on = beta >= 0.0;
-        active[q] = on;
-        rz[q] = rzn[q];
-        (void)rz;
+        double beta = 0.0;
+        if (active[q]) {
+          beta = fast_div(rzn[q], rz[q]);
+          rz[q] = rzn[q];
+          if (!(rzn[q] > tol2[q])) active[q] = false;
+        }
         HMX_UNROLL
-        for (int c = 0; c < D; ++c) pv[q * D + c] = on ? fma(beta, pv[q * D + c], z[q * D + c]) : 0.0;
+        for (int c = 0; c < D; ++c)
+          if (own) p_own[q * D + c] = active[q] ? fma(beta, p_own[q * D + c], z[q * D + c]) : 0.0;
       }
-      publish(pv);
     }
 
     // ---- 6. epilogue: A_hom[p][q] = <C>[p][q] - b_p . x_q - x_p . r_q  (all in scaled variables) ----
-    cluster_sync();  // nobody reads p or the matrix any more (also orders the last publish before the overwrite)
+    cluster_sync();  // nobody reads p or the matrix any more
     double* s_x = s_p;                  // [NOWN][NVEC] (own slots only, packed)
     double* s_r = s_K;                  // [NOWN][NVEC]
     double* s_b = s_K + NOWN * NVEC;    // [NOWN][NVEC]
@@ -762,6 +834,14 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
     if (P.chi != nullptr && own) {  // correctors x = L^-T x~ in natural node order: [q][component][node]
       constexpr int NN = NM * NM * NM;
       const int nat = cx + NM * (cy + NM * zg);
+      // inverse of the packed lower-triangular factor
+      double Li[6];
+      Li[0] = 1.0 / Lf[0];
+      Li[2] = 1.0 / Lf[2];
+      Li[5] = 1.0 / Lf[5];
+      Li[1] = -Lf[1] * Li[0] * Li[2];
+      Li[4] = -Lf[4] * Li[2] * Li[5];
+      Li[3] = -(Lf[3] * Li[0] + Lf[4] * Li[1]) * Li[5];
       HMX_UNROLL
       for (int q = 0; q < NRL; ++q) {
         HMX_UNROLL
@@ -771,6 +851,14 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
           for (int s = c; s < D; ++s) v += Li[cl_tri(s, c)] * xt[q * D + s];
           P.chi[((size_t)pt * NRHS * D + (h * NRL + q) * D + c) * NN + nat] = v;
         }
+      }
+    }
+    // iteration statistics of all right-hand sides: one thread of each half of node 0
+    if (rank == 0 && t_id < TPN) {
+      HMX_UNROLL
+      for (int q = 0; q < NRL; ++q) {
+        s_xch[t_id * NRL + q] = (double)it[q];
+        s_xch[8 + t_id * NRL + q] = rz0[q] > P.atol * P.atol ? sqrt(rz[q] / rz0[q]) : 0.0;
       }
     }
     cluster_sync();
@@ -790,14 +878,6 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
       if (P.A_hom != nullptr)
         for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
       if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
-    }
-    // iteration statistics: thread 0 holds its own half's counters; the other half's come through shared memory
-    if (rank == 0 && t_id < TPN) {
-      HMX_UNROLL
-      for (int q = 0; q < NRL; ++q) s_xch[t_id * NRL + q] = (double)it[q];
-    }
-    sync();
-    if (rank == 0 && t_id == 0) {
       int itmax = 0;
       unsigned long long tot = 0;
       double worst = 0.0;
@@ -805,7 +885,7 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
         const int iq = (int)s_xch[qq];
         itmax = iq > itmax ? iq : itmax;
         tot += (unsigned long long)iq;
-        if (rz0_all[qq] > P.atol * P.atol) worst = fmax(worst, sqrt(rz_all[qq] / rz0_all[qq]));
+        worst = fmax(worst, s_xch[8 + qq]);
       }
       if (P.iters != nullptr) P.iters[pt] = itmax;
       if (P.resid != nullptr) P.resid[pt] = worst;

@@ -40,6 +40,12 @@ struct __attribute__((aligned(16))) U4 {
   unsigned x, y, z, w;
 };
 
+// compile-time integer passed as a value (generic lambdas over stencil directions)
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
+
 // ---- Kuhn tables ------------------------------------------------------------------
 template <int D>
 HMX_HOSTDEV constexpr int kuhn_ntypes() { return D == 2 ? 2 : 6; }

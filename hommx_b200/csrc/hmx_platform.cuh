@@ -13,6 +13,7 @@
 #else
 
 #define HMX_DEV __device__ __forceinline__
+#define HMX_DEV_NOINLINE __device__ __noinline__  // large set-up routines called from several places: one copy of the code
 #define HMX_HOSTDEV __host__ __device__ __forceinline__
 #define HMX_GLOBAL(maxthreads, minblocks) __global__ void __launch_bounds__(maxthreads, minblocks)
 // a kernel launched as thread-block clusters of `cl` CTAs (compile-time cluster size: a plain launch forms the clusters)
@@ -150,6 +151,21 @@ HMX_DEV T* cluster_map(T* p, int rank) {
   unsigned long long out;
   asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
   return reinterpret_cast<T*>(out);
+}
+// shared::cluster address (32-bit) of the location `p` of this CTA's shared memory in the CTA of rank `rank`
+HMX_DEV unsigned cluster_map_u32(const void* p, int rank) {
+  unsigned out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(smem_u32(p)), "r"(rank));
+  return out;
+}
+// bulk copy of this CTA's shared memory into the shared memory of CTA `rank` (DSMEM, issued to the copy engine by one
+// thread: UBLKCP); dst / bar are given as the addresses of the same objects in THIS CTA and are mapped to the peer.
+// Completion is signalled on the PEER's mbarrier as transaction bytes.  bytes multiple of 16, addresses 16-byte aligned.
+HMX_DEV void bulk_s2c(void* dst, const void* src, unsigned bytes, MBar* bar, int rank) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   cluster_map_u32(dst, rank)),
+               "r"(smem_u32(src)), "r"(bytes), "r"(cluster_map_u32(bar, rank))
+               : "memory");
 }
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 // busy-wait for about `cycles` SM clocks (CS2R on the clock register): staggers the right-hand-side groups of a CTA

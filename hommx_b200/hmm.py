@@ -152,9 +152,11 @@ class BaseHMM:
         # cubes (csrc/hmx_cell_common.cuh, Grid<.., COLL>); False solves the full n^d cell
         self._collapse = bool(collapse_invariant_axes)
         # "pcg": the matrix-free PCG kernels; "direct": dense Cholesky per cell (elasticity cells of <= 192 unknowns,
-        # csrc/hmx_cell_dense.cuh); "auto": direct where the PCG iteration count of a sample of macro cells says it pays
-        if cell_solver not in ("auto", "pcg", "direct"):
-            raise ValueError("cell_solver must be 'auto', 'pcg' or 'direct'")
+        # csrc/hmx_cell_dense.cuh); "cluster": PCG on the assembled stencil resident in a thread-block cluster's
+        # distributed shared memory (3-D elasticity, full cells; csrc/hmx_cell_cluster.cuh); "auto": direct where the
+        # PCG iteration count of a sample of macro cells says it pays, cluster for cells that exceed one SM
+        if cell_solver not in ("auto", "pcg", "direct", "cluster"):
+            raise ValueError("cell_solver must be 'auto', 'pcg', 'direct' or 'cluster'")
         self._cell_solver = cell_solver
         self.cell_solver_used = None
         self._shard = bool(shard)  # False: assemble every macro cell on this GPU even if torch.distributed is up
@@ -203,8 +205,11 @@ class BaseHMM:
         can_direct = native.dense_fits(self._program, self._structure.n, native.collapse_mask(self._program, self._collapse))
         if self._cell_solver == "direct" and not can_direct:
             raise native.HmxError(f"cell_solver='direct' holds at most {native.DENSE_MAX_DOF} unknowns per micro cell")
-        self._solver = mk(native.DENSE if self._cell_solver == "direct" else None)
-        self.cell_solver_used = "direct" if self._solver.variant == native.DENSE else "pcg"
+        forced = {"direct": native.DENSE, "cluster": native.CLUSTER, "pcg": native.MATRIX_FREE}.get(self._cell_solver)
+        if self._cell_solver == "cluster":
+            self._collapse = False  # the cluster kernel solves the full cell
+        self._solver = mk(forced)
+        self.cell_solver_used = {native.DENSE: "direct", native.CLUSTER: "cluster"}.get(self._solver.variant, "pcg")
         tdev = torch.device("cuda", self._device)
         # device state in LOCAL numbering: the nodes this rank's cells reference, the CSR slots they touch (+ 1 dummy)
         sh = assembly.build_local_shard(self._msh.cells, self._pattern.slot_map, self._pattern.nnz, self._rank, self._world)

@@ -155,8 +155,15 @@ def default_variant(prog, n, collapse=False):
     cell fits it (by default the drop-in classes decide from measured PCG iterations: hmm.py, cell_solver="auto")."""
     if prog.kind == POISSON:
         return MATRIX_FREE
-    if os.environ.get("HMX_ELASTICITY_VARIANT") == "dense" and dense_fits(prog, n, collapse_mask(prog, collapse)):
+    coll = collapse_mask(prog, collapse)
+    if os.environ.get("HMX_ELASTICITY_VARIANT") == "dense" and dense_fits(prog, n, coll):
         return DENSE
+    # cells that exceed one SM (3-D, n >= 10: the matrix-free kernel would keep its vectors in L2): the assembled
+    # stencil resident in the distributed shared memory of a thread-block cluster, where a portable cluster (<= 8
+    # CTAs) holds it (measured on B200, 10^3 fibre cell: 7.8k against 5.8k cell solves/s; profiles/r02_cluster.md)
+    if prog.dim == 3 and coll == 0 and vectors_in_l2(prog, n, 0) and os.environ.get("HMX_ELASTICITY_VARIANT") != "matrix-free":
+        if 2 <= cluster_size(prog, n) <= 8:
+            return CLUSTER
     return MATRIX_FREE
 
 
@@ -172,21 +179,26 @@ def cluster_tpn():
     return int(os.environ.get("HMX_TPN", "2"))
 
 
-def cluster_coarse_dofs(prog, n, threads=512):
+def cluster_coarse_dofs(prog, n, cl, threads=512):
     """Unknowns of the cluster kernel's coarse space (mirrors ``ClusterLayout::TWO`` in csrc/hmx_cell_cluster.cuh): the
-    level-1 space summed along micro axis 0 when the coefficient does not depend on it; 0 = block Jacobi only."""
+    level-1 space summed along micro axis 0 when the coefficient does not depend on it and the set-up scratch fits in
+    one CTA's share of the matrix area; 0 = block Jacobi only."""
     if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" or n % 2 or n < 4 or threads // 6 < 32:
         return 0
     h = n // 2
-    if 3 * h**3 <= 96 or (prog.ydep & 1):
+    if 3 * h**3 <= 96 or (prog.ydep & 1) or 3 * h * h > 96:
         return 0
-    return 3 * h * h if 3 * h * h <= 96 else 0
+    ndep = bin(prog.ydep & 7).count("1")
+    setup = 27 * 3 * 3 * h**3 + max(1, prog.natoms) * 6 * h**ndep
+    if setup > 63 * (n // cl) * n * n + 36 * n * n:
+        return 0
+    return 3 * h * h
 
 
 def cluster_threads(prog, n, cl):
     own = (n // cl) * n * n * cluster_tpn()
     nt = 32 * (-(-own // 32))
-    ncd = cluster_coarse_dofs(prog, n)
+    ncd = cluster_coarse_dofs(prog, n, cl)
     return max(nt, 64, 32 * (-(-(6 * ncd + 6) // 32)) if ncd else 0)
 
 
@@ -195,8 +207,8 @@ def cluster_smem_bytes(prog, n, cl):
     nt = cluster_threads(prog, n, cl)
     pz, npl = n // cl, n * n
     nown, npb = pz * npl, (pz + 2) * npl
-    ncd = cluster_coarse_dofs(prog, n, nt) or 2
-    two = cluster_coarse_dofs(prog, n, nt) > 0
+    ncd = cluster_coarse_dofs(prog, n, cl, nt) or 2
+    two = cluster_coarse_dofs(prog, n, cl, nt) > 0
     nrec = (max(6 * ncd + 6, 36) + 1) // 2 * 2
     nblk = (ncd + 31) // 32
     cbuf = 0
@@ -205,7 +217,7 @@ def cluster_smem_bytes(prog, n, cl):
         cbuf = max(3 * pad + 2, 6 * ncd) + 2
     work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36)
     ntri = ncd * (ncd + 1) // 2 if two else 0
-    doubles = (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
+    doubles = 4 + (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
     return 8 * doubles
 
 

@@ -13,11 +13,17 @@ import cases as K
 from hommx_b200 import native
 
 names = sys.argv[1:] or ["e3_fibre_rot_n4", "e3_fibre_rot_n8_c4"]
+import dataclasses
+
 for nm in names:
+    nm, _, nover = nm.partition(":")  # "case[:n]": the case's coefficient on an n^3 cell
     case = K.BY_NAME[nm]
+    if nover:
+        case = dataclasses.replace(case, n=int(nover), threads=None)
+        nm = f"{nm}[n={case.n}]"
     prog = K.program(case)
     qp, qw = K.tables(case, prog)
-    npts = 148 * 8
+    npts = 148 * (8 if case.n <= 8 else 2)
     x = K.points(case, npts)
     xd = torch.tensor(x, device="cuda")
     out = {}

@@ -11,6 +11,7 @@
 #include <stddef.h>
 
 #define HMX_DEV inline
+#define HMX_DEV_NOINLINE inline
 #define HMX_HOSTDEV inline
 #define HMX_RESTRICT __restrict__
 #define HMX_UNROLL
@@ -188,6 +189,12 @@ inline T* cluster_map(T* p, int rank) {
   emu::Cta* c = emu::g_cta;
   const size_t off = (size_t)((const char*)p - (const char*)c->smem);
   return reinterpret_cast<T*>((char*)c->peers[rank].smem + off);
+}
+inline void bulk_s2c(void* dst, const void* src, unsigned bytes, MBar* bar, int rank) {
+  __builtin_memcpy(cluster_map(static_cast<char*>(dst), rank), src, bytes);  // lands "instantly" (see bulk_g2s)
+  MBar* rb = cluster_map(bar, rank);
+  rb->tx -= bytes;
+  mbar_maybe_complete(rb);
 }
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void spin_cycles(long long) {}  // timing only: nothing to emulate

@@ -1,0 +1,212 @@
+"""The cluster variant of the 3-D elasticity cell kernel (csrc/hmx_cell_cluster.cuh: assembled block stencil resident
+in the distributed shared memory of a thread-block cluster, BASELINE north star (2)).
+
+CPU (`not gpu`): the unmodified kernel source in the fiber emulator, whose cluster support runs the CTAs of a cluster
+in one scheduler with DSMEM as pointers into the peers' buffers -- against the oracle and the committed golden vectors,
+and under forward / reverse / random fiber schedules (a race in the halo exchange, the receive buffers or the set-up
+aliasing shows up as a schedule-dependent result).
+GPU: through the C ABI against the committed golden vectors, the oracle and the matrix-free kernel; bit-identical
+results for different grid sizes; the drop-in class with cell_solver="cluster"."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases as K
+from hommx_b200 import native
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cpu_emu"))
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_vectors.json")))
+CASES_3D = ["e3_fibre_rot_n4", "e3_cubic_shear_n4", "e3_hooke_smooth_shear_n6", "e3_fibre_rot_n8_c4"]
+
+
+def test_host_side_sizing_mirrors_the_kernel_layout():
+    """cluster_size / cluster_threads / cluster_smem_bytes (native.py) against what the kernel's static layout says."""
+    import emu
+
+    for name, n in (("e3_fibre_rot_n4", 4), ("e3_fibre_rot_n8_c4", 8)):
+        prog = K.program(K.BY_NAME[name])
+        cl = native.cluster_size(prog, n)
+        lib = emu.build(prog, n, None, native.CLUSTER)
+        info = (emu.C.c_int * 8)()
+        lib.hmx_emu_info(info)
+        assert lib.hmx_emu_cluster() == cl
+        assert info[1] == native.cluster_threads(prog, n, cl)
+        assert abs(info[0] - native.cluster_smem_bytes(prog, n, cl)) <= 64  # (alignment padding)
+        assert info[0] <= native.SMEM_LIMIT
+    prog = K.program(K.BY_NAME["e3_fibre_rot_n8_c4"])
+    assert native.cluster_size(prog, 8) == 2 and native.cluster_coarse_dofs(prog, 8, 2) == 48
+    assert native.cluster_size(prog, 10) == 5 and native.cluster_coarse_dofs(prog, 10, 5) == 0
+    with pytest.raises(native.HmxError):
+        native.resolve(K.program(K.BY_NAME["p3_smooth_n4"]), 4, variant=native.CLUSTER)
+
+
+@pytest.mark.parametrize("name", ["e3_fibre_rot_n4", "e3_cubic_shear_n4"])
+def test_emulated_cluster_kernel_matches_oracle(name):
+    import emu
+
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    mic = K.oracle_cell(case, prog)
+    x = K.points(case, 2)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-11, variant=native.CLUSTER, grid=4)
+    A, it, res = s.cell_tensors(x, return_stats=True)
+    for k in range(len(x)):
+        ref = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(A[k] - ref).max() <= case.tol * np.abs(ref).max()
+    assert (it > 0).all() and (res <= 1e-7).all()  # (the absolute tolerance ends these solves)
+
+
+def test_emulated_cluster_kernel_two_level_matches_golden_vectors():
+    """The 8^3 fibre cell: 2 CTAs per cluster, semi-coarsened two-level preconditioner, bulk-copied halo planes."""
+    import emu
+
+    name = "e3_fibre_rot_n8_c4"
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-10, variant=native.CLUSTER, grid=4)
+    A, it, res = s.cell_tensors(np.array(GOLD[name]["x"]), return_stats=True)
+    for k, ref in enumerate(GOLD[name]["A_hom"]):
+        assert np.abs(A[k] - np.array(ref)).max() <= 1e-10 * np.abs(np.array(ref)).max()
+    assert it.max() < 230  # (block Jacobi alone needs ~ 400 at this tolerance)
+
+
+def test_emulated_cluster_kernel_correctors_and_local_matrix():
+    import emu
+
+    case = K.BY_NAME["e3_fibre_rot_n4"]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    x = K.points(case, 1)
+    cl = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-12, variant=native.CLUSTER, grid=2)
+    mf = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-12, variant=native.MATRIX_FREE, threads=case.threads)
+    a, b = cl.correctors(x), mf.correctors(x)
+    a = a - a.mean(axis=(-1, -2, -3), keepdims=True)  # correctors are defined up to a constant
+    b = b - b.mean(axis=(-1, -2, -3), keepdims=True)
+    assert np.abs(a - b).max() <= 1e-9 * np.abs(b).max()
+    cells, xyz = K.random_simplices(3, 2)
+    Sa, _ = cl.local_matrices(cells, xyz)
+    Sb, _ = mf.local_matrices(cells, xyz)
+    assert np.abs(Sa - Sb).max() <= 1e-11 * np.abs(Sb).max()
+
+
+@pytest.mark.parametrize("name", ["e3_fibre_rot_n4", "e3_fibre_rot_n8_c4"])
+def test_emulated_cluster_kernel_is_schedule_independent(name, monkeypatch):
+    import emu
+
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    x = K.points(case, 1)
+    out = []
+    for order in ("forward", "reverse", "shuffle:7"):
+        monkeypatch.setenv("HMX_EMU_ORDER", order)
+        monkeypatch.setenv("HMX_EMU_POISON", "1")
+        s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-9, variant=native.CLUSTER, grid=2)
+        out.append(s.cell_tensors(x))
+    assert np.isfinite(out[0]).all()
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in GOLD if K.BY_NAME[n].kind == 1 and K.BY_NAME[n].dim == 3 and K.BY_NAME[n].n % 2 == 0])
+def test_cluster_kernel_matches_golden_vectors(name):
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-10, variant=native.CLUSTER)
+    assert s.info["cluster"] >= 2 and s.info["resident_clusters"] >= 1
+    Ah = s.cell_tensors(np.array(GOLD[name]["x"]))
+    for k, A in enumerate(GOLD[name]["A_hom"]):
+        assert np.abs(Ah[k] - np.array(A)).max() <= 1e-10 * np.abs(np.array(A)).max()
+    s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES_3D)
+def test_cluster_kernel_matches_oracle_and_matrix_free(name):
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    npts = 40
+    x = K.points(case, npts, seed=11)
+    cl = native.CellSolver(prog, case.n, qp, qw, rtol=1e-10, variant=native.CLUSTER)
+    mf = native.CellSolver(prog, case.n, qp, qw, rtol=1e-10, variant=native.MATRIX_FREE, threads=case.threads)
+    A, it, res = cl.cell_tensors(x, return_stats=True)
+    B = mf.cell_tensors(x)
+    scale = np.abs(B).max(axis=(1, 2), keepdims=True)
+    assert (np.abs(A - B) / scale).max() <= 1e-10
+    assert (it > 0).all() and (res <= 1e-7).all()
+    mic = K.oracle_cell(case, prog)
+    for k in range(2 if case.heavy else 4):
+        ref = K.oracle_tensor(case, mic, x[k])
+        assert np.abs(A[k] - ref).max() <= case.tol * np.abs(ref).max()
+    cells, xyz = K.random_simplices(3, 6)
+    Sa, _ = cl.local_matrices(cells, xyz)
+    Sb, _ = mf.local_matrices(cells, xyz)
+    assert np.abs(Sa - Sb).max() <= 1e-10 * np.abs(Sb).max()
+    cl.close()
+    mf.close()
+
+
+@pytest.mark.gpu
+def test_cluster_kernel_large_cell_replaces_the_l2_fallback():
+    """10^3 cell (288 KB of vectors: exceeds one SM): 5 CTAs per cluster by default, same tensors as the matrix-free
+    kernel that keeps its vectors in L2."""
+    case = K.BY_NAME["e3_fibre_rot_n10_l2"]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    assert native.default_variant(prog, case.n, collapse=False) == native.CLUSTER
+    x = K.points(case, 12, seed=5)
+    cl = native.CellSolver(prog, case.n, qp, qw, rtol=1e-9)
+    assert cl.variant == native.CLUSTER and cl.info["cluster"] == 5
+    mf = native.CellSolver(prog, case.n, qp, qw, rtol=1e-9, variant=native.MATRIX_FREE)
+    A, B = cl.cell_tensors(x), mf.cell_tensors(x)
+    assert np.abs(A - B).max() <= 1e-9 * np.abs(B).max()
+    cl.close()
+    mf.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["e3_fibre_rot_n4", "e3_fibre_rot_n8_c4"])
+def test_cluster_kernel_is_bitwise_reproducible(name):
+    """Fixed reduction orders across warps, CTAs and the cluster (rank order): repeated runs and different numbers of
+    resident clusters give bit-identical tensors."""
+    case = K.BY_NAME[name]
+    prog = K.program(case)
+    qp, qw = K.tables(case, prog)
+    x = K.points(case, 64, seed=2)
+    s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-9, variant=native.CLUSTER)
+    a = s.cell_tensors(x)
+    b = s.cell_tensors(x)
+    s.set_grid(2 * s.info["cluster"])
+    c = s.cell_tensors(x)
+    s.set_grid(7 * s.info["cluster"])
+    d = s.cell_tensors(x)
+    assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d)
+    s.close()
+
+
+@pytest.mark.gpu
+def test_drop_in_class_with_cluster_solver():
+    """LinearElasticityStratifiedHMM(cell_solver="cluster") assembles the same macro matrix as the default."""
+    import coefficients as Cf
+    from hommx_b200 import LinearElasticityStratifiedHMM, mesh
+    from hommx_b200 import ufl as pufl
+
+    m = mesh.create_box((0.0, 0.0, 0.0), (1.0, 0.4, 0.1), (3, 2, 1))
+    mic = mesh.create_unit_cube(8, 8, 8)
+    f = lambda x: pufl.as_vector([0.0, 0.0, -0.01])  # noqa: E731
+    kw = dict(petsc_options_cell_problem={"ksp_rtol": 1e-10})
+    a = LinearElasticityStratifiedHMM(m, Cf.hooke_fibre_3d(pufl), f, mic, 0.01, Cf.dtheta_rotation_3d(pufl), cell_solver="cluster", **kw)
+    b = LinearElasticityStratifiedHMM(m, Cf.hooke_fibre_3d(pufl), f, mic, 0.01, Cf.dtheta_rotation_3d(pufl), cell_solver="pcg",
+                                      collapse_invariant_axes=False, **kw)
+    a._assemble_stiffness()
+    b._assemble_stiffness()
+    assert a.cell_solver_used == "cluster" and b.cell_solver_used == "pcg"
+    assert np.abs(a._A_values - b._A_values).max() <= 1e-9 * np.abs(b._A_values).max()
