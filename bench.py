@@ -330,11 +330,15 @@ def run_ours(args, rank, world, local_rank):
         todo = [("c4", False, "auto", "strong"), ("c3", False, "auto", "strong"), (args.workload, True, "auto", "weak")]
         if world == 1:
             todo += [("c2", False, "auto", "weak"), ("c3", False, "auto", "weak"), ("c4s", False, "auto", "weak"),
-                     ("c4", True, "pcg", "weak"), ("c3", True, "auto", "weak"), ("c2", True, "auto", "weak")]  # fmt: skip
+                     ("c4", True, "pcg", "weak"), ("c3", True, "auto", "weak"), ("c2", True, "auto", "weak"),
+                     # the cluster-resident assembled stencil (csrc/hmx_cell_cluster.cuh): opt-in on the 8^3 cell, the
+                     # default where the cell exceeds one SM (10^3), next to the matrix-free kernel on the same cell
+                     ("c4", False, "cluster", "weak"), ("c4n10", False, "auto", "weak"), ("c4n10", False, "pcg", "weak")]  # fmt: skip
         for name, collapse, how, scaling in todo:
             if name == args.workload and not collapse and scaling == SCALING:
                 continue
-            key = name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "") + ("_strong" if scaling == "strong" else "")
+            key = (name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "") + ("_cluster" if how == "cluster" else "")
+                   + ("_strong" if scaling == "strong" else ""))  # fmt: skip
             try:
                 other[key] = quick_rate(name, local_rank, collapse, world, how, scaling)
             except Exception as e:  # never lose the headline line
@@ -473,6 +477,7 @@ def quick_rate(name, device, collapse=False, world=1, cell_solver="auto", scalin
     return {"desc": WORKLOADS[name]["desc"], "micro_problem": note, "macro_cells": n_all, "n_gpus": world, "scaling": scaling,
             "macro_assembly_wall_ms": best, "ms_per_step": best,
             "cell_solves_per_s": n_all / (best * 1e-3), "cell_solver": hmm.cell_solver_used,
+            "ctas_per_cluster": sol.info["cluster"], "resident_clusters": sol.info["resident_clusters"],
             "mean_pcg_iterations": float(d["it"].float().mean().item())}  # fmt: skip
 
 

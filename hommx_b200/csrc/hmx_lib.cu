@@ -7,6 +7,7 @@
 // The macro gather, halo pack/unpack and the peak microbenchmarks are compiled in.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -695,6 +696,49 @@ int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_
   HMX_CUDA(h, guard.status);
   hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
   HMX_CUDA(h, cudaGetLastError());
+  return HMX_OK;
+}
+
+namespace {
+// ncclAllReduce of the NCCL library the HOST already uses (the communicator is the host's): looked up among the loaded
+// objects first, then libnccl.so.2 by name.  libhmx.so has no link-time dependency on NCCL.
+typedef int (*nccl_allreduce_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+nccl_allreduce_fn find_nccl_allreduce(std::string& why) {
+  static nccl_allreduce_fn fn = nullptr;
+  if (fn) return fn;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+  if (!sym) {
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (lib) sym = dlsym(lib, "ncclAllReduce");
+  }
+  if (!sym) why = "ncclAllReduce not found: load the NCCL library the communicator belongs to before calling hmx_halo_sum_dev";
+  fn = reinterpret_cast<nccl_allreduce_fn>(sym);
+  return fn;
+}
+}  // namespace
+
+int hmx_halo_sum_dev(hmx_t* h, void* nccl_comm, double* csr_vals, const int64_t* slots, int64_t n, double* buf) {
+  if (!h) return HMX_ERR_ARG;
+  if (!nccl_comm) return fail(h, HMX_ERR_ARG, "hmx_halo_sum: null communicator");
+  if (n < 0 || (n > 0 && (!csr_vals || !slots || !buf))) return fail(h, HMX_ERR_ARG, "hmx_halo_sum: null buffer");
+  std::string why;
+  nccl_allreduce_fn allreduce = find_nccl_allreduce(why);
+  if (!allreduce) return fail(h, HMX_ERR_KERNEL, "%s", why.c_str());
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
+  // every rank must enter the collective, also one that shares no slot (n = 0 is a zero-length all-reduce)
+  if (n > 0) {
+    hmx_halo_pack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
+    HMX_CUDA(h, cudaGetLastError());
+  }
+  const int nccl_float64 = 8, nccl_sum = 0;  // ncclDataType_t / ncclRedOp_t of nccl.h (stable since NCCL 2.0)
+  const int rc = allreduce(buf, buf, (size_t)n, nccl_float64, nccl_sum, nccl_comm, h->stream);
+  if (rc != 0) return fail(h, HMX_ERR_CUDA, "ncclAllReduce failed with ncclResult_t %d", rc);
+  if (n > 0) {
+    hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
+    HMX_CUDA(h, cudaGetLastError());
+  }
   return HMX_OK;
 }
 

@@ -31,7 +31,7 @@ _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "
 MATRIX_FREE, DENSE, CLUSTER = 0, 3, 4  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
-ABI_VERSION = 5  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
+ABI_VERSION = 6  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -55,7 +55,7 @@ def build_library(force=False, verbose=False):
     deps = [src, os.path.join(INCLUDE, "hmx.h")] + [os.path.join(CSRC, h) for h in _HEADERS[:2]]
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
         return LIB_PATH
-    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+    cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl",
            "-o", LIB_PATH, src]  # fmt: skip
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -99,6 +99,7 @@ SYMBOLS = {
     "hmx_rhs_iterations": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.c_int32]),
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_halo_sum_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_macro_load_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "hmx_macro_lift_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -593,6 +594,11 @@ class CellSolver:
         v = C.c_int64()
         self._check(self.lib.hmx_rhs_iterations(self._h, C.byref(v), 1 if reset else 0))
         return v.value
+
+    def halo_sum_dev(self, nccl_comm, csr_vals, slots, n, buf):
+        """pack + ncclAllReduce + unpack on the handle's stream; ``nccl_comm`` is a raw ncclComm_t (an int address)."""
+        dp = self._dp
+        self._check(self.lib.hmx_halo_sum_dev(self._h, C.c_void_p(int(nccl_comm)), dp(csr_vals), dp(slots), int(n), dp(buf)))
 
     def macro_load_dev(self, image, n_cells, cell_nodes, node_xyz, qp, qw, Fe):
         """Element load vectors Fe [n_cells][(dim+1)*bs] of the right-hand side compiled into ``image``."""

@@ -105,6 +105,10 @@ WORKLOADS = {
     "c1": dict(cls="PoissonHMM", dim=2, kind=0, n=16, coeff="smooth_sin", dtheta=None,
                box=((0.0, 0.0), (1.0, 1.0)), cells=(32, 32), strong_cells=(32, 32), eps=2.0**-5,
                desc="BASELINE configs[0]: PoissonHMM 2D, 32x32 macro mesh, 16x16 micro cell"),
+    "c4n10": dict(cls="LinearElasticityStratifiedHMM", dim=3, kind=1, n=10, coeff="hooke_fibre_3d", dtheta="dtheta_rotation_3d",
+                  box=((0.0, 0.0, 0.0), (1.0, 0.4, 0.1)), cells=(20, 8, 2), strong_cells=(20, 8, 2), eps=0.01,
+                  desc="C4's beam and coefficient on a 10^3 micro cell (its vectors exceed one SM; not a BASELINE config): "
+                       "cluster-resident stencil against the matrix-free kernel with its vectors in L2"),
     "c4s": dict(cls="LinearElasticityStratifiedHMM", dim=3, kind=1, n=8, coeff="hooke_spheres_3d", dtheta="dtheta_rotation_3d",
                 box=((0.0, 0.0, 0.0), (1.0, 0.4, 0.1)), cells=(40, 16, 4), strong_cells=(80, 32, 8), eps=0.01,
                 desc="C4's beam with a periodic stiff BALL instead of the fibre (coefficient varies along all three "
@@ -158,6 +162,12 @@ def kernel_jobs():
         A, Dt = coefficient(name, pufl)
         prog = codegen.build_program(A, w["dim"], w["kind"], Dt)
         jobs.append((prog, w["n"], None))
+        if w["kind"] == 1 and w["dim"] == 3:  # full cell: both PCG kernels (bench: "*_cluster" / "*_pcg" entries)
+            from hommx_b200 import native
+
+            jobs.append((prog, w["n"], None, False, True, None, native.MATRIX_FREE, False))
+            if native.cluster_size(prog, w["n"]) >= 2:
+                jobs.append((prog, w["n"], None, False, True, None, native.CLUSTER, False))
         if prog.ydep != (1 << w["dim"]) - 1:
             jobs.append((prog, w["n"], None, False, True, None, None, True))  # axis-collapsed variant (other_workloads)
     return jobs

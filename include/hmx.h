@@ -31,7 +31,7 @@ typedef struct hmx_handle hmx_t;
 /* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
  * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
  * to new Python sources would otherwise be called with the wrong arguments). */
-#define HMX_ABI_VERSION 5
+#define HMX_ABI_VERSION 6
 int32_t hmx_abi_version(void);
 
 enum hmx_status {
@@ -132,6 +132,13 @@ int hmx_rhs_iterations(hmx_t* h, int64_t* total, int32_t reset);
  * back.  All pointers are device pointers. */
 int hmx_halo_pack_dev(hmx_t* h, const double* csr_vals, const int64_t* slots, int64_t n, double* buf);
 int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_t n, const double* buf);
+/* The whole exchange for a host that holds an NCCL communicator (SURVEY 8b proposal `hmx_halo_sum`; replaces the PETSc
+ * assembly of shared rows, hmm.py:442): pack, ncclAllReduce(buf, n doubles, sum) on the handle's stream, unpack.
+ * `nccl_comm` is the caller's ncclComm_t; libhmx looks ncclAllReduce up in the NCCL library already loaded in the
+ * process (no link-time dependency).  Every rank of the communicator must call it, with the same n (the shared-slot
+ * list is global: slots touched by more than one rank, in the same order everywhere).  All pointers are device
+ * pointers. */
+int hmx_halo_sum_dev(hmx_t* h, void* nccl_comm, double* csr_vals, const int64_t* slots, int64_t n, double* buf);
 
 /* the macro load vector on the device.  Replaces the FFCx kernel behind
  * `_assemble_vector_array(b_local.array_w, self._L, ...)` (hmm.py:445-450; L = inner(f(x), v) dx, hmm.py:131-133).

@@ -34,6 +34,44 @@ for name in ("poisson3d", "elasticity3d"):
     print(f"[rank {rank}] {name}: world={world} cells {sharded._dev['lo']}..{sharded._dev['hi']} shared slots {n_shared} "
           f"of {len(a)}  max rel diff sharded vs single {err:.2e}", flush=True)  # fmt: skip
     ok = ok and err < 1e-13
+
+
+def raw_nccl_comm():
+    """An ncclComm_t made with the NCCL library torch has loaded (ctypes), as a host without torch would hold one."""
+    import ctypes as C
+    import glob
+
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*")) + ["libnccl.so.2"]
+    lib = C.CDLL(cands[0], mode=C.RTLD_GLOBAL)
+    uid = (C.c_byte * 128)()
+    if rank == 0:
+        assert lib.ncclGetUniqueId(C.byref(uid)) == 0
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    uid = (C.c_byte * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+    comm = C.c_void_p()
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_byte * 128, C.c_int]
+    assert lib.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    return lib, comm
+
+
+# hmx_halo_sum_dev: the exchange through the C ABI with a raw ncclComm_t equals the torch.distributed all-reduce
+if world > 1:
+    lib, comm = raw_nccl_comm()
+    halo = sharded._dev["halo"]
+    vals = sharded._dev["vals"]
+    torch.manual_seed(rank)
+    vals.copy_(torch.rand_like(vals))
+    a = vals.clone()
+    halo.sum(a)  # pack + torch all-reduce + unpack
+    b = vals.clone()
+    sharded._solver.set_stream(torch.cuda.current_stream().cuda_stream)
+    sharded._solver.halo_sum_dev(comm.value, b, halo.slots, halo.n, torch.zeros_like(halo.buf))
+    torch.cuda.synchronize()
+    same = bool(torch.equal(a, b))
+    print(f"[rank {rank}] hmx_halo_sum_dev (raw ncclComm_t) == torch all-reduce on {halo.n} shared slots: {same}", flush=True)
+    ok = ok and same
+    lib.ncclCommDestroy(comm)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -147,9 +147,12 @@ def test_cluster_kernel_matches_oracle_and_matrix_free(name):
         ref = K.oracle_tensor(case, mic, x[k])
         assert np.abs(A[k] - ref).max() <= case.tol * np.abs(ref).max()
     cells, xyz = K.random_simplices(3, 6)
-    Sa, _ = cl.local_matrices(cells, xyz)
-    Sb, _ = mf.local_matrices(cells, xyz)
-    assert np.abs(Sa - Sb).max() <= 1e-10 * np.abs(Sb).max()
+    nb2 = cl.nb * cl.nb
+    gp = np.arange(len(cells) * nb2 + 1, dtype=np.int64)  # identity gather: slot j <- S_flat[j]
+    gs = np.arange(len(cells) * nb2, dtype=np.int32)
+    va, Sa = cl.assemble_macro(cells, xyz, gp, gs, want_local=True)
+    vb, Sb = mf.assemble_macro(cells, xyz, gp, gs, want_local=True)
+    assert np.abs(Sa - Sb).max() <= 1e-10 * np.abs(Sb).max() and np.array_equal(va, Sa.ravel())
     cl.close()
     mf.close()
 

@@ -128,7 +128,9 @@ def test_kernel_choice_for_elasticity_cells():
     assert native.resolve(c4, 8)[:3] == (384, 1, native.MATRIX_FREE)  # PCG stays the default variant
     # full 3-D cells: threads chosen so that every warp owns whole planes of the last axis (block sweep)
     assert native.default_threads(3, 1, 8) == 384 and native.default_threads(3, 1, 10) == 192 and native.default_threads(3, 1, 12) == 384
-    assert native.resolve(c4, 6)[:2] == (192, 2) and native.resolve(c4, 10)[:2] == (192, 1)
+    assert native.resolve(c4, 6)[:2] == (192, 2) and native.resolve(c4, 10, variant=native.MATRIX_FREE)[:2] == (192, 1)
+    # cells that exceed one SM go to the cluster-resident stencil where a portable cluster holds them (10^3: 5 CTAs)
+    assert native.resolve(c4, 10)[:3] == (416, 1, native.CLUSTER) and native.resolve(c4, 12)[2] == native.MATRIX_FREE
     poisson = K.program(K.BY_NAME["p2_smooth_n8"])
     assert not native.dense_fits(poisson, 8)
     m3 = mesh.create_unit_cube(2, 2, 2)
