@@ -16,6 +16,29 @@
 
 namespace hmx {
 
+// General periodic micro mesh for the element-list kernel (hmx_cell_generic.cuh): any simplicial mesh
+// of the unit box whose boundary nodes match periodically (cell_problem.py:16-35 of the reference accepts any such
+// mesh).  Built on the host (hommx_b200/micro.py: element_list_tables); all pointers are device pointers.
+struct MicroMesh {
+  int n_elem, n_nodes, nnzb, nq;  // elements, PERIODIC nodes, blocks of the node-node pattern, quadrature points per element
+  const int* elem_nodes;    // [n_elem][D+1] periodic node ids
+  const double* elem_grad;  // [n_elem][D+1][D] gradients of the P1 basis functions
+  const double* elem_vol;   // [n_elem]
+  const double* elem_yq;    // [n_elem][nq][D] quadrature points (micro coordinates)
+  const int* row_ptr;       // [n_nodes + 1] block rows of the periodic stiffness pattern
+  const int* col;           // [nnzb]
+  const int* blk_ptr;       // [nnzb + 1] contributions of every block, in a fixed order
+  const int* blk_src;       //   (e * (D+1) + a) * (D+1) + b: element e couples its local vertices a (row) and b (column)
+  const int* node_ptr;      // [n_nodes + 1] elements around every node
+  const int* node_src;      //   e * (D+1) + a
+  const int* diag;          // [n_nodes] block index of (i, i)
+};
+// doubles of per-CTA global scratch of the element-list kernel
+HMX_HOSTDEV constexpr long long element_list_scratch(int n_elem, int n_nodes, int nnzb, int natoms1, int bs, int nrhs) {
+  return (long long)natoms1 * n_elem + (long long)nnzb * bs * bs + (long long)n_nodes * bs * bs +
+         5LL * nrhs * n_nodes * bs;  // atoms, matrix blocks, inverse diagonal blocks, b x r p y
+}
+
 struct CellParams {
   long long n_pts;         // macro quadrature points (= macro cells in fused mode)
   const double* x_pts;     // [n_pts][3] macro points, or nullptr when cells are given
@@ -33,6 +56,7 @@ struct CellParams {
   int nq;
   int max_it;
   double rtol, atol;
+  const MicroMesh* mesh;  // element-list kernel only (device pointer), else nullptr
 };
 
 // 16-byte word for packed index tables (one LDS.128)

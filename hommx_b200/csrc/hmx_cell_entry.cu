@@ -5,8 +5,8 @@
 // The same file, compiled by g++ with -DHMX_EMULATE, is the CPU emulation used by the
 // `not gpu` tests (tests/cpu_emu) -- test infrastructure, never shipped.
 #ifndef HMX_VARIANT
-#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel (PCG), 3 = dense Cholesky, 4 = cluster-resident stencil
-#endif
+#define HMX_VARIANT 0  // elasticity: 0 = matrix-free element kernel (PCG), 3 = dense Cholesky, 4 = cluster-resident stencil;
+#endif                 // both kinds: 5 = element-list kernel for general periodic micro meshes (the mesh is data: HMX_NM = 0)
 #ifndef HMX_CLUSTER
 #define HMX_CLUSTER 1  // CTAs per thread-block cluster (variant 4: the cell is split into z-slabs over the cluster)
 #endif
@@ -29,6 +29,7 @@
 #include "hmx_cell_cluster.cuh"
 #endif
 #endif
+#include "hmx_cell_generic.cuh"
 #include HMX_COEFF_FILE
 
 #ifndef HMX_MINB
@@ -42,7 +43,9 @@
 #endif
 
 namespace {
-#if HMX_KIND == 0
+#if HMX_VARIANT == 5
+using Layout = hmx::GenericLayout<HMX_COEFF, HMX_NT>;
+#elif HMX_KIND == 0
 using Layout = hmx::PoissonLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
 using Layout = hmx::ElasticityAsmLayout<HMX_COEFF, HMX_NM, HMX_NT>;
@@ -56,10 +59,10 @@ using Layout = hmx::ClusterLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_CLUSTER, HMX_TP
 using Layout = hmx::ElasticityLayout<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>;
 #endif
 #ifndef HMX_EXPERIMENTAL_VARIANTS
-static_assert(HMX_KIND == 0 || HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_VARIANT == 4,
-              "elasticity kernel variants: 0 (matrix-free PCG), 3 (dense Cholesky) or 4 (cluster-resident stencil)");
+static_assert(HMX_KIND == 0 || HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_VARIANT == 4 || HMX_VARIANT == 5,
+              "elasticity kernel variants: 0 (matrix-free PCG), 3 (dense Cholesky), 4 (cluster-resident stencil), 5 (element list)");
 #endif
-static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled variants have no collapsed form");
+static_assert(HMX_VARIANT == 0 || HMX_VARIANT == 3 || HMX_COLL == 0, "the assembled / element-list variants have no collapsed form");
 static_assert(HMX_VARIANT == 4 || HMX_CLUSTER == 1, "only variant 4 is launched as thread-block clusters");
 static_assert(HMX_COEFF::KIND == HMX_KIND, "coefficient program / kernel kind mismatch");
 constexpr int kSmemBytes = Layout::total * 8;
@@ -73,7 +76,9 @@ extern "C" HMX_GLOBAL_CLUSTER(HMX_NT, HMX_CLUSTER) hmx_cell(const hmx::CellParam
 }
 #else
 extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
-#if HMX_KIND == 0
+#if HMX_VARIANT == 5
+  hmx::generic_cell_body<HMX_COEFF, HMX_NT>(P);
+#elif HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);
@@ -87,14 +92,17 @@ extern "C" HMX_GLOBAL(HMX_NT, HMX_MINB) hmx_cell(const hmx::CellParams P) {
 }
 #endif
 // 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 quadrature degree,
-// 8 CTAs per cluster (1: ordinary launch; the grid must be a multiple of it), 9-11 reserved
+// 8 CTAs per cluster (1: ordinary launch; the grid must be a multiple of it), 9 atoms of the coefficient program,
+// 10-11 reserved
 extern "C" __device__ const int hmx_info[12] = {kSmemBytes, HMX_NT, Layout::NRHS, HMX_COEFF::DIM, HMX_KIND, HMX_NM,
-                                                kScratch, HMX_COEFF::QDEG, HMX_CLUSTER, 0, 0, 0};
+                                                kScratch, HMX_COEFF::QDEG, HMX_CLUSTER, HMX_COEFF::NATOMS, 0, 0};
 #else
 #include "emu_runtime.h"
 static void emu_body(void* arg) {
   const hmx::CellParams& P = *static_cast<const hmx::CellParams*>(arg);
-#if HMX_KIND == 0
+#if HMX_VARIANT == 5
+  hmx::generic_cell_body<HMX_COEFF, HMX_NT>(P);
+#elif HMX_KIND == 0
   hmx::poisson_cell_body<HMX_COEFF, HMX_NM, HMX_NT, HMX_COLL, HMX_VGLOB>(P);
 #elif HMX_VARIANT == 1 && defined(HMX_EXPERIMENTAL_VARIANTS)
   hmx::elasticity_asm_cell_body<HMX_COEFF, HMX_NM, HMX_NT>(P);

@@ -237,6 +237,10 @@ struct hmx_handle {
   double rtol = 1e-8, atol = 1e-10;
   int max_it = 10000;
   int info[8] = {0};
+  // element-list kernel: the micro mesh on the device
+  DevBuf mm_buf[11], mm_struct;
+  int natoms = 1;  // hmx_info[9] of the kernel image: atoms of the coefficient program (element-list scratch)
+  long long mm_scratch = 0;  // per-CTA scratch doubles for this mesh
   int cluster = 1;       // CTAs per thread-block cluster of the cell kernel (hmx_info[8]; 1: ordinary launch)
   int max_clusters = 0;  // clusters of the cell kernel that are resident at once
   int grid_override = 0;
@@ -310,7 +314,7 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
     ncl = std::max<long long>(1, std::min<long long>(ncl, n_pts));
     grid = ncl * h->cluster;
   }
-  const size_t scratch_doubles = (size_t)h->info[7] * (size_t)grid;
+  const size_t scratch_doubles = (size_t)(h->mm_scratch > 0 ? h->mm_scratch : h->info[7]) * (size_t)grid;
   if (scratch_doubles) HMX_CUDA(h, h->scratch.reserve(scratch_doubles * sizeof(double)));
   hmx::CellParams P;
   P.n_pts = n_pts;
@@ -330,6 +334,7 @@ int launch_cell(hmx_t* h, long long n_pts, const double* x_pts, const int* cell_
   P.max_it = h->max_it;
   P.rtol = h->rtol;
   P.atol = h->atol;
+  P.mesh = h->mm_scratch > 0 ? h->mm_struct.as<hmx::MicroMesh>() : nullptr;
   void* args[] = {&P};
   HMX_CU(h, driver().LaunchKernel(h->fn, (unsigned)grid, 1, 1, (unsigned)h->info[1], 1, 1, (unsigned)h->info[0],
                                   (CUstream)h->stream, args, nullptr));
@@ -349,8 +354,12 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
   *out = nullptr;
   if (d->dim != 2 && d->dim != 3) return fail(nullptr, HMX_ERR_ARG, "Topology should be 3D or 2D");  // hmm.py:104-105
   if (d->kind != HMX_POISSON && d->kind != HMX_ELASTICITY) return fail(nullptr, HMX_ERR_ARG, "unknown problem kind %d", d->kind);
-  if (d->n_micro < 2) return fail(nullptr, HMX_ERR_ARG, "the periodic micro mesh needs at least 2 cells per axis");
-  if (d->nq < 1 || !d->qp || !d->qw) return fail(nullptr, HMX_ERR_ARG, "quadrature table missing");
+  const hmx_micro_mesh* um = d->micro_mesh;
+  if (!um && d->n_micro < 2) return fail(nullptr, HMX_ERR_ARG, "the periodic micro mesh needs at least 2 cells per axis");
+  if (um && (um->n_elem < 1 || um->n_nodes < 1 || um->nnzb < um->n_nodes || !um->elem_nodes || !um->elem_grad || !um->elem_vol ||
+             !um->elem_yq || !um->row_ptr || !um->col || !um->blk_ptr || !um->blk_src || !um->node_ptr || !um->node_src || !um->diag))
+    return fail(nullptr, HMX_ERR_ARG, "incomplete micro mesh description");
+  if (d->nq < 1 || (!um && !d->qp) || !d->qw) return fail(nullptr, HMX_ERR_ARG, "quadrature table missing");
   if (!d->kernel_image || d->kernel_image_size == 0)
     return fail(nullptr, HMX_ERR_KERNEL, "no cell kernel image: the CUDA path has no fallback");
   int ndev = 0;
@@ -368,7 +377,7 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
   hmx_t* h = new hmx_t;
   h->dim = d->dim;
   h->kind = d->kind;
-  h->n_micro = d->n_micro;
+  h->n_micro = um ? 0 : d->n_micro;
   h->nq = d->nq;
   h->device = d->device;
   h->rtol = d->rtol;
@@ -405,7 +414,7 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
       return bail(HMX_ERR_CUDA);
     }
     // ki: 0 smem bytes, 1 threads, 2 nrhs, 3 dim, 4 kind, 5 n_micro, 6 scratch doubles per CTA, 7 reserved
-    if (ki[3] != d->dim || ki[4] != d->kind || ki[5] != d->n_micro) {
+    if (ki[3] != d->dim || ki[4] != d->kind || ki[5] != h->n_micro) {
       fail(h, HMX_ERR_KERNEL, "kernel image was built for dim=%d kind=%d n=%d, descriptor says dim=%d kind=%d n=%d", ki[3], ki[4],
            ki[5], d->dim, d->kind, d->n_micro);
       return bail(HMX_ERR_KERNEL);
@@ -429,6 +438,7 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
     }
     h->info[5] = per_sm;
     h->cluster = ki[8] > 1 ? ki[8] : 1;
+    h->natoms = ki[9] > 0 ? ki[9] : 1;
     if (h->cluster > 1) {
       // the kernel carries its cluster size (__cluster_dims__): a plain launch of a multiple of it forms the clusters
       if (h->cluster > 8) {
@@ -472,12 +482,55 @@ int hmx_create(hmx_t** out, const hmx_desc* d) {
     return bail(HMX_ERR_CUDA);
   }
   h->own_stream = true;
-  const size_t nqp = (size_t)h->ntypes() * d->nq * d->dim;
+  const size_t nqp = um ? 1 : (size_t)h->ntypes() * d->nq * d->dim;
   if (h->qp.reserve(nqp * sizeof(double)) != cudaSuccess || h->qw.reserve(d->nq * sizeof(double)) != cudaSuccess ||
-      cudaMemcpy(h->qp.p, d->qp, nqp * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess ||
+      (!um && cudaMemcpy(h->qp.p, d->qp, nqp * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) ||
       cudaMemcpy(h->qw.p, d->qw, d->nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
     fail(h, HMX_ERR_CUDA, "uploading the quadrature table failed: %s", cudaGetErrorString(cudaGetLastError()));
     return bail(HMX_ERR_CUDA);
+  }
+  if (um) {  // the general micro mesh: copy every array, then the struct of device pointers
+    const int nv = d->dim + 1;
+    const size_t E = (size_t)um->n_elem, N = (size_t)um->n_nodes, Z = (size_t)um->nnzb;
+    const size_t nblk = (size_t)um->blk_ptr[Z], nnode = (size_t)um->node_ptr[N];
+    const void* src[11] = {um->elem_nodes, um->elem_grad, um->elem_vol, um->elem_yq, um->row_ptr, um->col,
+                           um->blk_ptr,    um->blk_src,   um->node_ptr, um->node_src, um->diag};
+    const size_t bytes[11] = {E * nv * sizeof(int), E * nv * d->dim * sizeof(double), E * sizeof(double),
+                              E * d->nq * d->dim * sizeof(double), (N + 1) * sizeof(int), Z * sizeof(int),
+                              (Z + 1) * sizeof(int), nblk * sizeof(int), (N + 1) * sizeof(int), nnode * sizeof(int), N * sizeof(int)};
+    if (nblk != E * nv * nv || nnode != E * nv) {
+      fail(h, HMX_ERR_ARG, "micro mesh: the contribution lists must hold every (element, vertex[, vertex]) once");
+      return bail(HMX_ERR_ARG);
+    }
+    for (int k = 0; k < 11; ++k)
+      if (h->mm_buf[k].reserve(std::max<size_t>(bytes[k], 8)) != cudaSuccess ||
+          cudaMemcpy(h->mm_buf[k].p, src[k], bytes[k], cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(h, HMX_ERR_CUDA, "uploading the micro mesh failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return bail(HMX_ERR_CUDA);
+      }
+    hmx::MicroMesh mm;
+    mm.n_elem = um->n_elem;
+    mm.n_nodes = um->n_nodes;
+    mm.nnzb = um->nnzb;
+    mm.nq = d->nq;
+    mm.elem_nodes = h->mm_buf[0].as<int>();
+    mm.elem_grad = h->mm_buf[1].as<double>();
+    mm.elem_vol = h->mm_buf[2].as<double>();
+    mm.elem_yq = h->mm_buf[3].as<double>();
+    mm.row_ptr = h->mm_buf[4].as<int>();
+    mm.col = h->mm_buf[5].as<int>();
+    mm.blk_ptr = h->mm_buf[6].as<int>();
+    mm.blk_src = h->mm_buf[7].as<int>();
+    mm.node_ptr = h->mm_buf[8].as<int>();
+    mm.node_src = h->mm_buf[9].as<int>();
+    mm.diag = h->mm_buf[10].as<int>();
+    if (h->mm_struct.reserve(sizeof mm) != cudaSuccess || cudaMemcpy(h->mm_struct.p, &mm, sizeof mm, cudaMemcpyHostToDevice) != cudaSuccess) {
+      fail(h, HMX_ERR_CUDA, "uploading the micro mesh failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return bail(HMX_ERR_CUDA);
+    }
+    const int bs = d->kind == HMX_POISSON ? 1 : d->dim;
+    h->mm_scratch = hmx::element_list_scratch(um->n_elem, um->n_nodes, um->nnzb, std::max(1, h->natoms), bs, h->info[2]);
+    h->info[7] = (int)std::min<long long>(h->mm_scratch, 2147483647LL);
   }
   if (h->work.reserve(sizeof(unsigned long long)) != cudaSuccess || cudaMemset(h->work.p, 0, sizeof(unsigned long long)) != cudaSuccess) {
     fail(h, HMX_ERR_CUDA, "allocating the work counter failed");
@@ -491,6 +544,8 @@ void hmx_destroy(hmx_t* h) {
   if (!h) return;
   DeviceGuard guard(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf& b : h->mm_buf) b.release();
+  h->mm_struct.release();
   for (DevBuf* b : {&h->qp, &h->qw, &h->scratch, &h->work, &h->d_x, &h->d_A, &h->d_it, &h->d_res, &h->d_cells, &h->d_xyz, &h->d_ptr,
                     &h->d_src, &h->d_vals, &h->d_S, &h->m_work, &h->l_qp, &h->l_qw})
     b->release();

@@ -137,10 +137,24 @@ class BaseHMM:
         self._petsc_options_prefix = petsc_options_prefix
 
         # ---- _setup_cell_problem_variables (hmm.py:178-207) ----
-        self._structure = micro.detect_structure(self._cell_mesh)
         self._program = codegen.build_program(A, self._tdim, self._KIND, Dtheta_transpose)
         pts, wts = quadrature_rule if quadrature_rule is not None else quadrature.default_rule(self._tdim, self._program.degree)
-        self._qp, self._qw = micro.quadrature_table(self._structure, pts, wts)
+        try:
+            # fast path: the structured simplicial split of the unit box (every mesh the reference's tests and examples use)
+            self._structure = micro.detect_structure(self._cell_mesh)
+            self._micro_tables = None
+            self._qp, self._qw = micro.quadrature_table(self._structure, pts, wts)
+        except ValueError as structured_only:
+            # any other periodic micro mesh (the reference's MPC path accepts every mesh with matching boundary nodes,
+            # cell_problem.py:16-35): the element-list kernel, csrc/hmx_cell_generic.cuh
+            try:
+                self._micro_tables = micro.ElementListTables(self._cell_mesh, pts, wts)
+            except ValueError as e:
+                raise ValueError(f"{e} (and not a structured grid: {structured_only})") from None
+            self._structure = None
+            self._qp, self._qw = None, self._micro_tables.qw
+            self._logger.info("general periodic micro mesh (%d elements, %d periodic nodes): element-list kernel",
+                              self._micro_tables.n_elem, self._micro_tables.n_nodes)
         self._cell_mesh_area = 1.0  # |Y| of the unit box (hmm.py:101)
 
         # ---- macro sparsity and slot map (replaces the un-preallocated AIJ of hmm.py:144-149) ----
@@ -198,18 +212,23 @@ class BaseHMM:
         if dev is None:
             dev = torch.cuda.current_device()
         self._device = int(dev)
+        general = self._micro_tables is not None
+        if general and self._cell_solver not in ("auto", "pcg"):
+            raise native.HmxError(f"cell_solver='{self._cell_solver}' needs the structured micro mesh")
         mk = lambda variant: native.CellSolver(  # noqa: E731
-            self._program, self._structure.n, self._qp, self._qw, rtol=self._cell_rtol, atol=self._cell_atol,
-            max_it=self._cell_max_it, device=self._device, collapse=self._collapse, variant=variant,
+            self._program, 0 if general else self._structure.n, self._qp, self._qw, rtol=self._cell_rtol, atol=self._cell_atol,
+            max_it=self._cell_max_it, device=self._device, collapse=self._collapse, variant=None if general else variant,
+            micro_tables=self._micro_tables,
         )  # fmt: skip
-        can_direct = native.dense_fits(self._program, self._structure.n, native.collapse_mask(self._program, self._collapse))
+        can_direct = not general and native.dense_fits(self._program, self._structure.n, native.collapse_mask(self._program, self._collapse))
         if self._cell_solver == "direct" and not can_direct:
             raise native.HmxError(f"cell_solver='direct' holds at most {native.DENSE_MAX_DOF} unknowns per micro cell")
         forced = {"direct": native.DENSE, "cluster": native.CLUSTER, "pcg": native.MATRIX_FREE}.get(self._cell_solver)
         if self._cell_solver == "cluster":
             self._collapse = False  # the cluster kernel solves the full cell
         self._solver = mk(forced)
-        self.cell_solver_used = {native.DENSE: "direct", native.CLUSTER: "cluster"}.get(self._solver.variant, "pcg")
+        self.cell_solver_used = {native.DENSE: "direct", native.CLUSTER: "cluster", native.ELEMENT_LIST: "pcg (element list)"}.get(
+            self._solver.variant, "pcg")  # fmt: skip
         tdev = torch.device("cuda", self._device)
         # device state in LOCAL numbering: the nodes this rank's cells reference, the CSR slots they touch (+ 1 dummy)
         sh = assembly.build_local_shard(self._msh.cells, self._pattern.slot_map, self._pattern.nnz, self._rank, self._world)
@@ -566,9 +585,13 @@ class PoissonPeriodicHMM:
         self._hmm._ensure_solver()
         A, chi = self._hmm._solver.cell_correctors(np.zeros((1, 3)))
         self._A_hom = A[0]
-        n, d = self._hmm._structure.n, self._tdim
-        ij = np.rint(self._cell_mesh.x[:, :d] * n).astype(np.int64) % n  # vertex -> periodic grid index
-        idx = tuple(ij[:, a] for a in reversed(range(d)))  # grid arrays are (z, y, x)
+        d = self._tdim
+        if self._hmm._micro_tables is not None:  # general mesh: values on the periodic nodes
+            idx = (self._hmm._micro_tables.node2per,)
+        else:
+            n = self._hmm._structure.n
+            ij = np.rint(self._cell_mesh.x[:, :d] * n).astype(np.int64) % n  # vertex -> periodic grid index
+            idx = tuple(ij[:, a] for a in reversed(range(d)))  # grid arrays are (z, y, x)
         V = fem.FunctionSpace(self._cell_mesh, 1)
         self._correctors = []
         for q in range(d):

@@ -27,11 +27,11 @@ KCACHE = os.path.join(_HERE, "_kcache")
 LIB_PATH = os.path.join(_HERE, "libhmx.so")
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "hmx_cell_coarse.cuh", "hmx_cell_elasticity.cuh",
-            "hmx_cell_dense.cuh", "hmx_cell_cluster.cuh", "hmx_cell_entry.cu")
-MATRIX_FREE, DENSE, CLUSTER = 0, 3, 4  # (1, 2: the slower assembled-operator experiments, experiments/assembled_operator/)
+            "hmx_cell_dense.cuh", "hmx_cell_cluster.cuh", "hmx_cell_generic.cuh", "hmx_cell_entry.cu")
+MATRIX_FREE, DENSE, CLUSTER, ELEMENT_LIST = 0, 3, 4, 5  # (1, 2: the slower assembled-operator experiments, experiments/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
-ABI_VERSION = 6  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
+ABI_VERSION = 7  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -65,12 +65,29 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+class hmx_micro_mesh(C.Structure):
+    _fields_ = [
+        ("n_elem", C.c_int32), ("n_nodes", C.c_int32), ("nnzb", C.c_int32),
+        ("elem_nodes", C.c_void_p), ("elem_grad", C.c_void_p), ("elem_vol", C.c_void_p), ("elem_yq", C.c_void_p),
+        ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("blk_ptr", C.c_void_p), ("blk_src", C.c_void_p),
+        ("node_ptr", C.c_void_p), ("node_src", C.c_void_p), ("diag", C.c_void_p),
+    ]  # fmt: skip
+
+    @classmethod
+    def from_tables(cls, t):
+        """``t``: hommx_b200.micro.ElementListTables (its arrays must outlive the call that uses the struct)."""
+        p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+        return cls(t.n_elem, t.n_nodes, t.nnzb, p(t.elem_nodes), p(t.elem_grad), p(t.elem_vol), p(t.elem_yq), p(t.row_ptr),
+                   p(t.col), p(t.blk_ptr), p(t.blk_src), p(t.node_ptr), p(t.node_src), p(t.diag))  # fmt: skip
+
+
 class hmx_desc(C.Structure):
     _fields_ = [
         ("dim", C.c_int32), ("kind", C.c_int32), ("n_micro", C.c_int32), ("nq", C.c_int32),
         ("qp", C.POINTER(C.c_double)), ("qw", C.POINTER(C.c_double)),
         ("kernel_image", C.c_void_p), ("kernel_image_size", C.c_size_t),
         ("rtol", C.c_double), ("atol", C.c_double), ("max_it", C.c_int32), ("device", C.c_int32),
+        ("micro_mesh", C.POINTER(hmx_micro_mesh)),
     ]  # fmt: skip
 
 
@@ -352,6 +369,8 @@ def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False
     coll = collapse_mask(prog, collapse) if variant in (MATRIX_FREE, DENSE) else 0
     if variant == DENSE and not dense_fits(prog, n, coll):
         raise HmxError(f"the dense variant holds at most {DENSE_MAX_DOF} unknowns per cell")
+    if variant == ELEMENT_LIST:  # general periodic micro mesh: the mesh is run-time data (n = 0)
+        return threads or 256, min_blocks or 2, variant, 0
     if variant == CLUSTER:
         if prog.kind == POISSON or prog.dim != 3:
             raise HmxError("the cluster variant is the 3-D elasticity kernel")
@@ -451,9 +470,18 @@ class CellSolver:
     """
 
     def __init__(self, prog: CoefficientProgram, n_micro, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, device=0, threads=None,
-                 min_blocks=None, variant=None, collapse=False):
+                 min_blocks=None, variant=None, collapse=False, micro_tables=None):
+        """``micro_tables`` (hommx_b200.micro.ElementListTables): a general periodic micro mesh -- the element-list
+        kernel (variant ELEMENT_LIST) is used, ``n_micro`` and ``qp`` are ignored."""
         self.prog = prog
         self.device = int(device)
+        self.micro_tables = micro_tables
+        if micro_tables is not None:
+            n_micro, variant, collapse = 0, ELEMENT_LIST, False
+            qw = micro_tables.qw
+            qp = np.zeros((2 if prog.dim == 2 else 6, len(qw), prog.dim))
+        elif variant == ELEMENT_LIST:
+            raise ValueError("the element-list kernel needs micro_tables")
         self.dim, self.kind, self.n = prog.dim, prog.kind, int(n_micro)
         self.m = prog.n_rhs
         self.nb = (self.dim + 1) * (1 if self.kind == POISSON else self.dim)
@@ -468,9 +496,10 @@ class CellSolver:
         T = 2 if self.dim == 2 else 6
         if qp.shape != (T, len(qw), self.dim):
             raise ValueError(f"quadrature points must have shape {(T, len(qw), self.dim)}, got {qp.shape}")
+        mm = hmx_micro_mesh.from_tables(micro_tables) if micro_tables is not None else None
         d = hmx_desc(self.dim, self.kind, self.n, len(qw), qp.ctypes.data_as(C.POINTER(C.c_double)),
                      qw.ctypes.data_as(C.POINTER(C.c_double)), C.cast(self._image, C.c_void_p), len(image),
-                     rtol, atol, max_it, device)  # fmt: skip
+                     rtol, atol, max_it, device, C.pointer(mm) if mm is not None else None)  # fmt: skip
         rc = self.lib.hmx_create(C.byref(self._h), C.byref(d))
         if rc != 0:
             msg = self.lib.hmx_last_error(None).decode()
@@ -566,6 +595,8 @@ class CellSolver:
         n, d = len(x), self.dim
         bs = 1 if self.kind == POISSON else d
         shape = [1 if (self.collapse_mask >> a) & 1 else self.n for a in range(d)]
+        if self.micro_tables is not None:  # general mesh: values on the periodic nodes, (n, n_rhs, bs, n_nodes)
+            shape = [self.micro_tables.n_nodes]
         dev = torch.device("cuda", self.device)  # the handle's device, whatever the caller's current device is
         with torch.cuda.device(dev):
             # the zero-fill and the uploads are torch work: the kernel must run on the same stream (or after them)
@@ -575,6 +606,8 @@ class CellSolver:
             chi = torch.zeros((n, self.m, bs) + tuple(reversed(shape)), dtype=torch.float64, device=dev)
             self._check(self.lib.hmx_cell_correctors_dev(self._h, n, self._dp(xd), self._dp(A), self._dp(chi)))
             self.sync()
+            if self.micro_tables is not None:
+                return A.cpu().numpy(), chi.cpu().numpy()
             full = (n, self.m, bs) + (self.n,) * d
             return A.cpu().numpy(), np.broadcast_to(chi.cpu().numpy(), full).copy()
 

@@ -31,7 +31,7 @@ typedef struct hmx_handle hmx_t;
 /* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
  * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
  * to new Python sources would otherwise be called with the wrong arguments). */
-#define HMX_ABI_VERSION 6
+#define HMX_ABI_VERSION 7
 int32_t hmx_abi_version(void);
 
 enum hmx_status {
@@ -48,10 +48,32 @@ enum hmx_kind { HMX_POISSON = 0, HMX_ELASTICITY = 1 };
 /* Describes one solver object = one (problem class, coefficient, micro mesh) combination;
  * replaces BaseHMM._setup_cell_problem_variables / _setup_cell_problem_forms
  * (hmm.py:178-207, 259-274). */
+/* General periodic micro mesh: any simplicial mesh of the unit box whose boundary nodes match
+ * periodically -- what create_periodic_boundary_conditions (cell_problem.py:16-300) accepts.  Replaces the structured
+ * n_micro^dim description for the element-list kernel (csrc/hmx_cell_generic.cuh, kernel images built with
+ * HMX_VARIANT=5).  HOST pointers; hmx_create copies everything to the device.  hommx_b200/micro.py
+ * (ElementListTables) builds these arrays from the mesh. */
+typedef struct hmx_micro_mesh {
+  int32_t n_elem;             /* micro elements */
+  int32_t n_nodes;            /* PERIODIC nodes (slaves identified with their masters) */
+  int32_t nnzb;               /* blocks of the node-node pattern of the periodic stiffness matrix */
+  const int32_t* elem_nodes;  /* [n_elem][dim+1] periodic node ids */
+  const double* elem_grad;    /* [n_elem][dim+1][dim] gradients of the P1 basis functions */
+  const double* elem_vol;     /* [n_elem] */
+  const double* elem_yq;      /* [n_elem][nq][dim] quadrature points in micro coordinates */
+  const int32_t* row_ptr;     /* [n_nodes+1] block rows */
+  const int32_t* col;         /* [nnzb] */
+  const int32_t* blk_ptr;     /* [nnzb+1] contributions of every block ... */
+  const int32_t* blk_src;     /* ... as (e*(dim+1) + a)*(dim+1) + b, in the order they are summed */
+  const int32_t* node_ptr;    /* [n_nodes+1] elements around every node ... */
+  const int32_t* node_src;    /* ... as e*(dim+1) + a */
+  const int32_t* diag;        /* [n_nodes] block index of (i, i) */
+} hmx_micro_mesh;
+
 typedef struct hmx_desc {
   int32_t dim;       /* 2 or 3 (micro and macro dimension agree, hmm.py:114-115) */
   int32_t kind;      /* hmx_kind */
-  int32_t n_micro;   /* cells per axis of the structured periodic micro mesh */
+  int32_t n_micro;   /* cells per axis of the structured periodic micro mesh (0 with micro_mesh) */
   int32_t nq;        /* quadrature points per micro element */
   const double* qp;  /* [T][nq][dim] points per element type, cube-local, units of h (T = dim!) */
   const double* qw;  /* [nq] weights, normalised to sum 1 */
@@ -64,6 +86,8 @@ typedef struct hmx_desc {
   double atol;
   int32_t max_it;    /* ksp_max_it */
   int32_t device;    /* CUDA device ordinal */
+  const hmx_micro_mesh* micro_mesh; /* NULL: the structured n_micro^dim mesh; else a general periodic mesh (qp is
+                                     * ignored then: the quadrature points are micro_mesh->elem_yq; qw still [nq]) */
 } hmx_desc;
 
 int hmx_create(hmx_t** out, const hmx_desc* desc);

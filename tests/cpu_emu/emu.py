@@ -22,7 +22,18 @@ class CellParams(C.Structure):
         ("n_pts", C.c_int64), ("x_pts", C.c_void_p), ("cell_nodes", C.c_void_p), ("node_xyz", C.c_void_p),
         ("A_hom", C.c_void_p), ("S_loc", C.c_void_p), ("iters", C.c_void_p), ("resid", C.c_void_p),
         ("qp", C.c_void_p), ("qw", C.c_void_p), ("scratch", C.c_void_p), ("chi", C.c_void_p), ("work", C.c_void_p),
-        ("nq", C.c_int32), ("max_it", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double),
+        ("nq", C.c_int32), ("max_it", C.c_int32), ("rtol", C.c_double), ("atol", C.c_double), ("mesh", C.c_void_p),
+    ]  # fmt: skip
+
+
+class MicroMesh(C.Structure):
+    """struct MicroMesh of csrc/hmx_cell_common.cuh (here with host pointers)."""
+
+    _fields_ = [
+        ("n_elem", C.c_int32), ("n_nodes", C.c_int32), ("nnzb", C.c_int32), ("nq", C.c_int32),
+        ("elem_nodes", C.c_void_p), ("elem_grad", C.c_void_p), ("elem_vol", C.c_void_p), ("elem_yq", C.c_void_p),
+        ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("blk_ptr", C.c_void_p), ("blk_src", C.c_void_p),
+        ("node_ptr", C.c_void_p), ("node_src", C.c_void_p), ("diag", C.c_void_p),
     ]  # fmt: skip
 
 
@@ -56,7 +67,16 @@ def build(prog, n, threads=None, variant=None, collapse=False):
 class EmuSolver:
     """Same call surface as hommx_b200.native.CellSolver's host entry points."""
 
-    def __init__(self, prog, n, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, threads=None, grid=4, variant=None, collapse=False):
+    def __init__(self, prog, n, qp, qw, rtol=1e-8, atol=1e-10, max_it=10000, threads=None, grid=4, variant=None, collapse=False,
+                 micro_tables=None):
+        self.tables = t = micro_tables
+        self.mesh = None
+        if t is not None:  # general periodic micro mesh: the element-list kernel
+            n, variant, collapse, qw = 0, native.ELEMENT_LIST, False, t.qw
+            qp = np.zeros((1, len(qw), prog.dim))
+            p = lambda a: a.ctypes.data  # noqa: E731
+            self.mesh = MicroMesh(t.n_elem, t.n_nodes, t.nnzb, t.nq, p(t.elem_nodes), p(t.elem_grad), p(t.elem_vol), p(t.elem_yq),
+                                  p(t.row_ptr), p(t.col), p(t.blk_ptr), p(t.blk_src), p(t.node_ptr), p(t.node_src), p(t.diag))  # fmt: skip
         self.prog, self.n = prog, n
         self.lib = build(prog, n, threads, variant, collapse)
         self.collapse = collapse
@@ -72,7 +92,12 @@ class EmuSolver:
     def _launch(self, P, n):
         cl = self.lib.hmx_emu_cluster()  # CTAs per thread-block cluster (1: ordinary launch)
         grid = cl * max(1, min(self.grid // cl if cl > 1 else self.grid, n))
-        scratch = np.zeros(max(1, self.info[6] * grid))
+        per_cta = self.info[6]
+        if self.tables is not None:
+            bs = 1 if self.prog.kind == 0 else self.prog.dim
+            per_cta = self.tables.scratch_doubles(self.prog.natoms, bs, self.m)
+            P.mesh = C.addressof(self.mesh)
+        scratch = np.zeros(max(1, per_cta * grid))
         P.scratch = scratch.ctypes.data
         P.qp, P.qw, P.nq = self.qp.ctypes.data, self.qw.ctypes.data, len(self.qw)
         P.max_it, P.rtol, P.atol = self.max_it, self.rtol, self.atol
@@ -95,6 +120,8 @@ class EmuSolver:
         d = self.prog.dim
         coll = native.collapse_mask(self.prog, self.collapse)
         shape = [1 if (coll >> a) & 1 else self.n for a in range(d)]
+        if self.tables is not None:
+            shape = [self.tables.n_nodes]
         bs = 1 if self.prog.kind == 0 else d
         chi = np.zeros((n, self.m, bs) + tuple(reversed(shape)))
         A = np.zeros((n, self.m, self.m))
