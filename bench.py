@@ -335,7 +335,7 @@ def run_ours(args, rank, world, local_rank):
                      # default where the cell exceeds one SM (10^3), next to the matrix-free kernel on the same cell
                      ("c4", False, "cluster", "weak"), ("c4n10", False, "auto", "weak"), ("c4n10", False, "pcg", "weak")]  # fmt: skip
         for name, collapse, how, scaling in todo:
-            if name == args.workload and not collapse and scaling == SCALING:
+            if name == args.workload and not collapse and scaling == SCALING and how == "auto":
                 continue
             key = (name + ("_axis_collapsed" if collapse else "") + ("_pcg" if how == "pcg" else "") + ("_cluster" if how == "cluster" else "")
                    + ("_strong" if scaling == "strong" else ""))  # fmt: skip

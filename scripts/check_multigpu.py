@@ -43,15 +43,22 @@ def raw_nccl_comm():
 
     cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so*")) + ["libnccl.so.2"]
     lib = C.CDLL(cands[0], mode=C.RTLD_GLOBAL)
-    uid = (C.c_byte * 128)()
+    class UniqueId(C.Structure):  # ncclUniqueId is passed BY VALUE: a struct, not an array
+        _fields_ = [("internal", C.c_byte * 128)]
+
+    uid = UniqueId()
     if rank == 0:
-        assert lib.ncclGetUniqueId(C.byref(uid)) == 0
+        rc = lib.ncclGetUniqueId(C.byref(uid))
+        assert rc == 0, f"ncclGetUniqueId -> {rc}"
     t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device="cuda")
     dist.broadcast(t, 0)
-    uid = (C.c_byte * 128).from_buffer_copy(bytes(t.cpu().tolist()))
+    uid = UniqueId.from_buffer_copy(bytes(t.cpu().tolist()))
     comm = C.c_void_p()
-    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_byte * 128, C.c_int]
-    assert lib.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    lib.ncclCommInitRank.restype = C.c_int
+    rc = lib.ncclCommInitRank(C.byref(comm), world, uid, rank)
+    assert rc == 0, f"ncclCommInitRank -> {rc}"
+    lib.ncclCommDestroy.argtypes = [C.c_void_p]
     return lib, comm
 
 
