@@ -93,7 +93,8 @@ struct ClusterLayout {
   static constexpr int o_u = o_scal + 8;                             // [NRHS][NCD] coarse solution
   // work area: line sums [NLINE][NVEC] -> then (after the exchange) the summed restricted residual [NRHS][NCD] and
   // the partial dot products [NRHS][NBLK]; also the column buffers of coarse_setup and the epilogue's partials
-  static constexpr int WORK = imax(imax(NLINE * NVEC, NRHS * NCD + NRHS * NBLK + 2), imax(TWO ? CS::CBUF : 0, EPART * NRHS * NRHS));
+  static constexpr int WORK = imax(imax(NLINE * NVEC, NRHS * NCD + NRHS * NBLK + 2),
+                                   imax(imax(TWO ? CS::CBUF : 0, EPART * NRHS * NRHS), NRHS * NRHS + NV * (D + 1) * D + 2));
   static constexpr int o_work = o_u + NRHS * NCD;
   static constexpr int o_ei = ((o_work + WORK + 1) / 2) * 2;         // [NTRI] inverse coarse matrix, packed
   static constexpr int o_p = ((o_ei + NTRI + 1) / 2) * 2;            // [NPB][NVEC]
@@ -862,34 +863,58 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
       }
     }
     cluster_sync();
-    if (rank == 0 && t_id == 0) {
-      double Ah[NRHS * NRHS];
-      for (int qq = 0; qq < NRHS; ++qq) {
-        double e[NV], sg[NV];
-        HMX_UNROLL
-        for (int v = 0; v < NV; ++v) e[v] = (v == qq) ? 1.0 : 0.0;
-        CO::stress(pc, smean, e, sg);
-        for (int p = 0; p < NRHS; ++p) {
-          double zsum = 0.0;
-          for (int rk = 0; rk < CL; ++rk) zsum += s_recv[rk * NREC + p * NRHS + qq];
-          Ah[p * NRHS + qq] = sg[p] - zsum;
+    if (rank == 0) {
+      // A_hom by thread 0, then one thread per entry of the macro element matrix
+      constexpr int NBM = (D + 1) * D;
+      double* s_ah = s_work;                 // [NRHS][NRHS]
+      double* s_cm = s_work + NRHS * NRHS;   // [NV][NBM] macro strain matrix, then |T|
+      if (t_id == 0) {
+        for (int qq = 0; qq < NRHS; ++qq) {
+          double e[NV], sg[NV];
+          HMX_UNROLL
+          for (int v = 0; v < NV; ++v) e[v] = (v == qq) ? 1.0 : 0.0;
+          CO::stress(pc, smean, e, sg);
+          for (int p = 0; p < NRHS; ++p) {
+            double zsum = 0.0;
+            for (int rk = 0; rk < CL; ++rk) zsum += s_recv[rk * NREC + p * NRHS + qq];
+            s_ah[p * NRHS + qq] = sg[p] - zsum;
+          }
+        }
+        if (P.S_loc != nullptr) {
+          double Cm[NV][NBM];
+          s_cm[NV * NBM] = macro_strain_matrix<D, 1>(verts, Cm);
+          HMX_UNROLL
+          for (int p = 0; p < NV; ++p)
+            HMX_UNROLL
+            for (int i = 0; i < NBM; ++i) s_cm[p * NBM + i] = Cm[p][i];
+        }
+        int itmax = 0;
+        unsigned long long tot = 0;
+        double worst = 0.0;
+        for (int qq = 0; qq < NRHS; ++qq) {
+          const int iq = (int)s_xch[qq];
+          itmax = iq > itmax ? iq : itmax;
+          tot += (unsigned long long)iq;
+          worst = fmax(worst, s_xch[8 + qq]);
+        }
+        if (P.iters != nullptr) P.iters[pt] = itmax;
+        if (P.resid != nullptr) P.resid[pt] = worst;
+        if (P.work != nullptr) atomic_add_u64(P.work, tot);
+      }
+      sync();
+      if (P.A_hom != nullptr)
+        for (int k = t_id; k < NRHS * NRHS; k += NT) P.A_hom[pt * NRHS * NRHS + k] = s_ah[k];
+      if (P.S_loc != nullptr) {
+        for (int k = t_id; k < NBM * NBM; k += NT) {
+          const int i = k / NBM, jj = k - i * NBM;
+          double acc = 0.0;  // same summation order as macro_element_matrix
+          HMX_UNROLL
+          for (int p = 0; p < NV; ++p)
+            HMX_UNROLL
+            for (int q2 = 0; q2 < NV; ++q2) acc += s_cm[p * NBM + jj] * s_ah[p * NRHS + q2] * s_cm[q2 * NBM + i];
+          P.S_loc[pt * NBM * NBM + k] = s_cm[NV * NBM] * acc;
         }
       }
-      if (P.A_hom != nullptr)
-        for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
-      if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
-      int itmax = 0;
-      unsigned long long tot = 0;
-      double worst = 0.0;
-      for (int qq = 0; qq < NRHS; ++qq) {
-        const int iq = (int)s_xch[qq];
-        itmax = iq > itmax ? iq : itmax;
-        tot += (unsigned long long)iq;
-        worst = fmax(worst, s_xch[8 + qq]);
-      }
-      if (P.iters != nullptr) P.iters[pt] = itmax;
-      if (P.resid != nullptr) P.resid[pt] = worst;
-      if (P.work != nullptr) atomic_add_u64(P.work, tot);
     }
     cluster_sync();  // shared memory (also the receive buffers the peers write into) is reused by the next point
   }

@@ -99,7 +99,7 @@ struct CoarseSpace {
   // on when the coarse unknowns fit, the set-up scratch fits in the p / y area, slots fit in 16 bits and the coarse
   // arrays fit in shared memory on top of everything else
   static constexpr bool ON = GEOM && NCD <= MAXDOF && ipow(2, D) * NC1 <= 65535 && setup_doubles <= 2 * NRHS * D * ipow(2, D) * NC1 &&
-                             BASE + NTRI + NPAR + CBUF <= SMEM_DOUBLES;
+                             BASE + NTRI + NPAR + CBUF + 128 <= SMEM_DOUBLES;  // (+ the epilogue area of the kernel)
   // level-1 class-0 slot of level-2 node C (natural index on the m2 grid; coordinate 0 along a summed-up axis)
   HMX_DEV static int slot2(int C) {
     int s = 0;

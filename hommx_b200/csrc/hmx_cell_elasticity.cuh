@@ -85,7 +85,8 @@ struct ElasticityLayout {
   using CS = CoarseSpace<CO, NM, NT, COLL, VGLOB, o_ei>;
   static constexpr int o_par = o_ei + (CS::ON ? CS::NTRI : 0);                           // [NP] 2 x 16-bit level-1 slots
   static constexpr int o_cbuf = o_par + (CS::ON ? (NP + 1) / 2 : 0);                     // [CS::CBUF]
-  static constexpr int total = o_cbuf + (CS::ON ? CS::CBUF : 0);
+  static constexpr int o_epi = ((o_cbuf + (CS::ON ? CS::CBUF : 0) + 1) / 2) * 2;  // epilogue: A_hom, macro strain matrix, |T|
+  static constexpr int total = o_epi + NRHS * NRHS + NV * (D + 1) * D + 2;
   static_assert(!CS::ON || (CS::setup_doubles <= 2 * NRHS * NDOF && !SUBW), "coarse set-up scratch must fit in the p / y area");
   static constexpr int scratch_doubles = (VGLOB ? 4 : 2) * NRHS * NDOF;  // x and r (and p, y) per CTA
   static_assert(NT % NRHS == 0 && NT % 32 == 0 && (TPR % 32 == 0 || 32 % TPR == 0),
@@ -1005,8 +1006,12 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
           for (int k = 0; k < NRHS * D; ++k) P.chi[((size_t)pt * NRHS * D + k) * NN + nat] = g_x[k * N + i];
         }
       }
+      // A_hom by thread 0, then one thread per entry of the macro element matrix (with one CTA per SM nothing would
+      // hide a serial 12 x 12 x 36 epilogue)
+      constexpr int NB = (D + 1) * D;
+      double* s_ah = sm + L::o_epi;         // [NRHS][NRHS]
+      double* s_cm = s_ah + NRHS * NRHS;    // [NV][NB] macro strain matrix, then |T|
       if (t_id == 0) {
-        double Ah[NRHS * NRHS];
         for (int qq = 0; qq < NRHS; ++qq) {
           double e[NV], sg[NV];
           HMX_UNROLL
@@ -1018,12 +1023,17 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
               z1 += buf[(qq * WPR + ww) * L::NREDV + p];
               z2 += buf[(qq * WPR + ww) * L::NREDV + NRHS + p];
             }
-            Ah[p * NRHS + qq] = sg[p] - z1 - z2;
+            s_ah[p * NRHS + qq] = sg[p] - z1 - z2;
           }
         }
-        if (P.A_hom != nullptr)
-          for (int k = 0; k < NRHS * NRHS; ++k) P.A_hom[pt * NRHS * NRHS + k] = Ah[k];
-        if (P.S_loc != nullptr) macro_element_matrix<D, 1>(verts, Ah, P.S_loc + pt * (D + 1) * D * (D + 1) * D);
+        if (P.S_loc != nullptr) {
+          double Cm[NV][NB];
+          s_cm[NV * NB] = macro_strain_matrix<D, 1>(verts, Cm);
+          HMX_UNROLL
+          for (int p = 0; p < NV; ++p)
+            HMX_UNROLL
+            for (int i = 0; i < NB; ++i) s_cm[p * NB + i] = Cm[p][i];
+        }
         int itmax = 0;
         unsigned long long tot = 0;
         double worst = 0.0;
@@ -1036,6 +1046,20 @@ HMX_DEV void elasticity_cell_body(const CellParams& P) {
         if (P.iters != nullptr) P.iters[pt] = itmax;
         if (P.resid != nullptr) P.resid[pt] = worst;
         if (P.work != nullptr) atomic_add_u64(P.work, tot);
+      }
+      sync();
+      if (P.A_hom != nullptr)
+        for (int k = t_id; k < NRHS * NRHS; k += NT) P.A_hom[pt * NRHS * NRHS + k] = s_ah[k];
+      if (P.S_loc != nullptr) {
+        for (int k = t_id; k < NB * NB; k += NT) {
+          const int i = k / NB, j = k - i * NB;
+          double acc = 0.0;  // same summation order as macro_element_matrix
+          HMX_UNROLL
+          for (int p = 0; p < NV; ++p)
+            HMX_UNROLL
+            for (int q2 = 0; q2 < NV; ++q2) acc += s_cm[p * NB + j] * s_ah[p * NRHS + q2] * s_cm[q2 * NB + i];
+          P.S_loc[pt * NB * NB + k] = s_cm[NV * NB] * acc;
+        }
       }
     }
     sync();  // shared memory and the scratch are reused by the next macro point

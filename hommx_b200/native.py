@@ -233,7 +233,7 @@ def cluster_smem_bytes(prog, n, cl):
     if two:
         pad = max((ncd + 15) // 16 * 16, -(-ncd // (nt // 16)) * (nt // 16))
         cbuf = max(3 * pad + 2, 6 * ncd) + 2
-    work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36)
+    work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36, 110)
     ntri = ncd * (ncd + 1) // 2 if two else 0
     doubles = 4 + (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
     return 8 * doubles

@@ -1,5 +1,6 @@
 """Hot source lines of a kernel: warp-stall samples of the SASS page of an .ncu-rep attributed to the source lines of
-the cubin's line table (nvdisasm -g).  usage: ncu_hot_lines.py report.ncu-rep kernel.cubin [top]"""
+the cubin's line table (nvdisasm -g); then the shared-memory wavefronts and the local-memory (spill) instructions per
+source line.  usage: ncu_hot_lines.py report.ncu-rep kernel.cubin [top]"""
 import collections
 import csv
 import re
@@ -46,3 +47,25 @@ for (key, n) in agg.most_common(top):
         if 0 < key[1] <= len(files[key[0]]):
             text = files[key[0]][key[1] - 1].strip()[:110]
     print(f"{100 * n / tot:5.1f}%  {inst[key]:>11d} inst  {key}  {text}")
+
+wi, wid = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
+wf, ideal, lcl = collections.Counter(), collections.Counter(), collections.Counter()
+for r in rows[2:]:
+    if len(r) <= wi:
+        continue
+    key = line_of.get(int(r[0], 16) - base, (None, ""))[0]
+    try:
+        wf[key] += int(r[wi])
+        ideal[key] += int(r[wid])
+    except ValueError:
+        pass
+    op = r[1].split()[0] if not r[1].strip().startswith("@") else r[1].split()[1]
+    if op.startswith(("LDL", "STL")) and r[ii].isdigit():
+        lcl[key] += int(r[ii])
+twf = sum(wf.values())
+print(f"shared-memory wavefronts: {twf} total")
+for key, n in wf.most_common(12):
+    print(f"{100 * n / max(twf, 1):5.1f}%  {n:>12d} (ideal {ideal[key]:>12d})  {key}")
+print("local-memory instructions (spills) by line:")
+for key, n in lcl.most_common(8):
+    print(f"{n:>12d}  {key}")
