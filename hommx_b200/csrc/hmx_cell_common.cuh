@@ -56,7 +56,11 @@ struct CellParams {
   int nq;
   int max_it;
   double rtol, atol;
-  const MicroMesh* mesh;  // element-list kernel only (device pointer), else nullptr
+#if !defined(HMX_VARIANT) || HMX_VARIANT == 5
+  // element-list kernel only (device pointer).  The host always passes the full structure; the other kernels are
+  // compiled with the prefix above (a kernel reads as many parameter bytes as it declares).
+  const MicroMesh* mesh;
+#endif
 };
 
 // 16-byte word for packed index tables (one LDS.128)

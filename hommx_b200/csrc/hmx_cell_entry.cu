@@ -29,7 +29,9 @@
 #include "hmx_cell_cluster.cuh"
 #endif
 #endif
+#if HMX_VARIANT == 5
 #include "hmx_cell_generic.cuh"
+#endif
 #include HMX_COEFF_FILE
 
 #ifndef HMX_MINB

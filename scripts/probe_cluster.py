@@ -27,7 +27,7 @@ for nm in names:
     x = K.points(case, npts)
     xd = torch.tensor(x, device="cuda")
     out = {}
-    for label, kw in (("matrix-free", dict(threads=case.threads)), ("cluster", dict(variant=native.CLUSTER))):
+    for label, kw in (("matrix-free", dict(threads=case.threads, variant=native.MATRIX_FREE)), ("cluster", dict(variant=native.CLUSTER))):
         s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-8, atol=1e-10, **kw)
         A = torch.zeros((npts, prog.n_rhs, prog.n_rhs), device="cuda", dtype=torch.float64)
         best = 1e9

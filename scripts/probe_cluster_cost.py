@@ -20,7 +20,7 @@ npts = 148 * 8
 xd = torch.tensor(K.points(case, npts), device="cuda")
 A = torch.empty((npts, prog.n_rhs, prog.n_rhs), device="cuda", dtype=torch.float64)
 for label in which:
-    kw = dict(variant=native.CLUSTER) if label == "cluster" else dict(threads=case.threads)
+    kw = dict(variant=native.CLUSTER) if label == "cluster" else dict(threads=case.threads, variant=native.MATRIX_FREE)
     s = native.CellSolver(prog, case.n, qp, qw, rtol=1e-8, atol=1e-10, **kw)
     units = s.info["resident_clusters"] or s.info["sms"] * s.info["ctas_per_sm"]
     prev = None
