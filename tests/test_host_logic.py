@@ -158,3 +158,37 @@ def test_nvrtc_compiles_the_cell_kernel_without_nvcc():
     prog = __import__("cases").program(__import__("cases").BY_NAME["p2_smooth_n8"])
     image = native.compile_kernel_nvrtc(prog, 8)
     assert image[:4] == b"\x7fELF" and len(image) > 10000
+
+
+def test_ctypes_structures_match_the_c_header(tmp_path):
+    """include/hmx.h is the boundary: the ctypes mirrors in native.py (hmx_desc, hmx_micro_mesh) must have the layout a C
+    compiler gives the header's structs, and the emulator's CellParams / MicroMesh the layout of csrc/hmx_cell_common.cuh."""
+    import ctypes as C
+    import subprocess
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "cpu_emu"))
+    import emu
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.cpp"
+    src.write_text(
+        '#include <cstddef>\n#include <cstdio>\n#define HMX_EMULATE 1\n#include "hmx.h"\n#include "hmx_cell_common.cuh"\n'
+        "int main() {\n"
+        '  printf("%zu %zu %zu %zu\\n", sizeof(hmx_desc), offsetof(hmx_desc, kernel_image), offsetof(hmx_desc, rtol), offsetof(hmx_desc, micro_mesh));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(hmx_micro_mesh), offsetof(hmx_micro_mesh, elem_nodes), offsetof(hmx_micro_mesh, diag));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(hmx::CellParams), offsetof(hmx::CellParams, nq), offsetof(hmx::CellParams, mesh));\n'
+        '  printf("%zu %zu %zu\\n", sizeof(hmx::MicroMesh), offsetof(hmx::MicroMesh, elem_nodes), offsetof(hmx::MicroMesh, diag));\n'
+        '  printf("%d\\n", HMX_ABI_VERSION);\n}\n'
+    )
+    exe = tmp_path / "layout"
+    r = subprocess.run(["g++", "-std=c++17", "-I", os.path.join(root, "include"), "-I", native.CSRC, "-I", os.path.join(root, "tests", "cpu_emu"),
+                        str(src), "-o", str(exe)], capture_output=True, text=True)  # fmt: skip
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = [[int(v) for v in ln.split()] for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines()]
+    d, m = native.hmx_desc, native.hmx_micro_mesh
+    assert got[0] == [C.sizeof(d), d.kernel_image.offset, d.rtol.offset, d.micro_mesh.offset]
+    assert got[1] == [C.sizeof(m), m.elem_nodes.offset, m.diag.offset]
+    assert got[2] == [C.sizeof(emu.CellParams), emu.CellParams.nq.offset, emu.CellParams.mesh.offset]
+    assert got[3] == [C.sizeof(emu.MicroMesh), emu.MicroMesh.elem_nodes.offset, emu.MicroMesh.diag.offset]
+    assert got[4] == [native.ABI_VERSION]
