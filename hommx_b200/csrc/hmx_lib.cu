@@ -66,11 +66,32 @@ __global__ void __launch_bounds__(256) hmx_lift(long long n, const long long* __
     b[i] = fixed ? ubc[i] : b[i] - acc;
   }
 }
-// Jacobi-PCG building blocks; scalars live in a small device array sc[]: 0 rz, 1 pAp, 2 rz_new, 3 rz0
+// Jacobi-PCG building blocks.  Scalars live in a small device array sc[]: 0 rz, 3 rz0; every dot product is reduced in
+// two FIXED-ORDER stages (block partials bp[blockIdx.x], then the same sum of the partials in every consumer block), so
+// the macro solve is bitwise reproducible like the assembly that feeds it (no floating-point atomics).
+__device__ __forceinline__ double hmx_block_sum_fixed(double v) {  // every thread of the block returns the same total
+  __shared__ double sh[33];
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+  __syncthreads();  // (sh may still be read from the previous call)
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+    sh[32] = s;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__device__ __forceinline__ double hmx_sum_partials(const double* __restrict__ bp, int g) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < g; i += blockDim.x) v += bp[i];
+  return hmx_block_sum_fixed(v);
+}
 __global__ void __launch_bounds__(256) hmx_pcg_init(long long n, const long long* __restrict__ ptr, const int* __restrict__ idx,
                                                     const double* __restrict__ vals, const double* __restrict__ b,
                                                     double* __restrict__ x, double* __restrict__ r, double* __restrict__ p,
-                                                    double* __restrict__ dinv, double* __restrict__ sc) {
+                                                    double* __restrict__ dinv, double* __restrict__ bp) {
   double part = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double d = 0.0;
@@ -83,15 +104,20 @@ __global__ void __launch_bounds__(256) hmx_pcg_init(long long n, const long long
     p[i] = di * b[i];
     part += b[i] * di * b[i];
   }
-  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&sc[0], part);
-    atomicAdd(&sc[3], part);
+  part = hmx_block_sum_fixed(part);
+  if (threadIdx.x == 0) bp[blockIdx.x] = part;
+}
+// sc[0] = sc[3] = sum of the init partials (one block)
+__global__ void __launch_bounds__(256) hmx_pcg_start(const double* __restrict__ bp, int g, double* __restrict__ sc) {
+  const double s = hmx_sum_partials(bp, g);
+  if (threadIdx.x == 0) {
+    sc[0] = s;
+    sc[3] = s;
   }
 }
 __global__ void __launch_bounds__(256) hmx_pcg_spmv(long long n, const long long* __restrict__ ptr, const int* __restrict__ idx,
                                                     const double* __restrict__ vals, const double* __restrict__ p,
-                                                    double* __restrict__ y, double* __restrict__ sc) {
+                                                    double* __restrict__ y, double* __restrict__ bp_pap) {
   double part = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     double acc = 0.0;
@@ -99,13 +125,15 @@ __global__ void __launch_bounds__(256) hmx_pcg_spmv(long long n, const long long
     y[i] = acc;
     part += p[i] * acc;
   }
-  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sc[1], part);
+  part = hmx_block_sum_fixed(part);
+  if (threadIdx.x == 0) bp_pap[blockIdx.x] = part;
 }
 __global__ void __launch_bounds__(256) hmx_pcg_update(long long n, double* __restrict__ x, double* __restrict__ r,
                                                       const double* __restrict__ p, const double* __restrict__ y,
-                                                      const double* __restrict__ dinv, double* __restrict__ sc) {
-  const double alpha = sc[1] > 0.0 ? sc[0] / sc[1] : 0.0;
+                                                      const double* __restrict__ dinv, const double* __restrict__ sc,
+                                                      const double* __restrict__ bp_pap, double* __restrict__ bp_rz) {
+  const double pAp = hmx_sum_partials(bp_pap, (int)gridDim.x);
+  const double alpha = pAp > 0.0 ? sc[0] / pAp : 0.0;
   double part = 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     x[i] += alpha * p[i];
@@ -113,19 +141,20 @@ __global__ void __launch_bounds__(256) hmx_pcg_update(long long n, double* __res
     r[i] = ri;
     part += ri * dinv[i] * ri;
   }
-  for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sc[2], part);
+  part = hmx_block_sum_fixed(part);
+  if (threadIdx.x == 0) bp_rz[blockIdx.x] = part;
 }
 __global__ void __launch_bounds__(256) hmx_pcg_direction(long long n, const double* __restrict__ r, double* __restrict__ p,
-                                                         const double* __restrict__ dinv, const double* __restrict__ sc) {
-  const double beta = sc[0] > 0.0 ? sc[2] / sc[0] : 0.0;
+                                                         const double* __restrict__ dinv, const double* __restrict__ sc,
+                                                         const double* __restrict__ bp_rz) {
+  const double rz_new = hmx_sum_partials(bp_rz, (int)gridDim.x);
+  const double beta = sc[0] > 0.0 ? rz_new / sc[0] : 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     p[i] = dinv[i] * r[i] + beta * p[i];
 }
-__global__ void hmx_pcg_rotate(double* sc) {  // rz <- rz_new, clear the accumulators of the next iteration
-  sc[0] = sc[2];
-  sc[1] = 0.0;
-  sc[2] = 0.0;
+__global__ void __launch_bounds__(256) hmx_pcg_rotate(double* sc, const double* __restrict__ bp_rz, int g) {  // rz <- rz_new
+  const double rz_new = hmx_sum_partials(bp_rz, g);
+  if (threadIdx.x == 0) sc[0] = rz_new;
 }
 // FP64 peak: 8 independent DFMA chains per thread, 1024 threads/SM
 __global__ void __launch_bounds__(256) hmx_dfma_peak(double* out, int iters, double a, double b) {
@@ -870,13 +899,15 @@ int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int
   DeviceGuard guard(h->device);
   HMX_CUDA(h, guard.status);
   const long long n = n_dofs;
-  HMX_CUDA(h, h->m_work.reserve((4 * (size_t)n + 8) * sizeof(double)));
+  const int g = grid_1d(n, 256, h->info[6]);
+  HMX_CUDA(h, h->m_work.reserve((4 * (size_t)n + 8 + 3 * (size_t)g) * sizeof(double)));
   double* r = h->m_work.as<double>();
   double *p = r + n, *y = p + n, *dinv = y + n, *sc = dinv + n;
-  const int g = grid_1d(n, 256, h->info[6]);
+  double *bp0 = sc + 8, *bp_pap = bp0 + g, *bp_rz = bp_pap + g;  // block partials of the three dot products
   const long long* ptr = (const long long*)indptr;
   HMX_CUDA(h, cudaMemsetAsync(sc, 0, 8 * sizeof(double), h->stream));
-  hmx_pcg_init<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, b, x, r, p, dinv, sc);
+  hmx_pcg_init<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, b, x, r, p, dinv, bp0);
+  hmx_pcg_start<<<1, 256, 0, h->stream>>>(bp0, g, sc);
   double hs[4] = {0, 0, 0, 0};
   HMX_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
   HMX_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -888,10 +919,10 @@ int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int
   while (rz > tol2 && it < max_it) {
     const int burst = std::min(16, max_it - it);  // the host looks at the residual every 16 iterations
     for (int k = 0; k < burst; ++k) {
-      hmx_pcg_spmv<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, p, y, sc);
-      hmx_pcg_update<<<g, 256, 0, h->stream>>>(n, x, r, p, y, dinv, sc);
-      hmx_pcg_direction<<<g, 256, 0, h->stream>>>(n, r, p, dinv, sc);
-      hmx_pcg_rotate<<<1, 1, 0, h->stream>>>(sc);
+      hmx_pcg_spmv<<<g, 256, 0, h->stream>>>(n, ptr, indices, csr_vals, p, y, bp_pap);
+      hmx_pcg_update<<<g, 256, 0, h->stream>>>(n, x, r, p, y, dinv, sc, bp_pap, bp_rz);
+      hmx_pcg_direction<<<g, 256, 0, h->stream>>>(n, r, p, dinv, sc, bp_rz);
+      hmx_pcg_rotate<<<1, 256, 0, h->stream>>>(sc, bp_rz, g);
     }
     it += burst;
     HMX_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof hs, cudaMemcpyDeviceToHost, h->stream));

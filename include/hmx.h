@@ -183,6 +183,7 @@ int hmx_macro_lift_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const in
                        const int8_t* bc_mask, const double* bc_values, double* b);
 /* Jacobi-preconditioned CG for the lifted (symmetric positive definite) macro system, x0 = 0; stops at
  * sqrt(r.z) <= max(rtol sqrt(r0.z0), atol) or max_it.  iters / resid are HOST pointers (may be NULL).
+ * Dot products are reduced in two fixed-order stages (no floating-point atomics): bitwise reproducible.
  * Synchronises the stream. */
 int hmx_macro_pcg_dev(hmx_t* h, int64_t n_dofs, const int64_t* indptr, const int32_t* indices, const double* csr_vals,
                       const double* b, double* x, double rtol, double atol, int32_t max_it, int32_t* iters, double* resid);
