@@ -27,6 +27,10 @@
 #pragma once
 #include "hmx_cell_common.cuh"
 
+#ifndef HMX_DENSE_LOOKAHEAD
+#define HMX_DENSE_LOOKAHEAD 1  // 1: publish column k + 1 early in the trailing update of step k; 0: after it (round-1 order);
+#endif                         // 2: the miscompiled form of 1 (repro only)
+
 namespace hmx {
 
 template <class CO, int NM, int NT, int COLL = 0>
@@ -271,6 +275,9 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
     HMX_UNROLL
     for (int p = 0; p < NRHS; ++p) brow[p] = (t_id < NDOF && t_id >= D) ? s_b[p * NPAD + t_id] : 0.0;
     double gram = 0.0;  // thread p * NRHS + q accumulates y_p . y_q
+#ifdef HMX_DENSE_DEBUG
+    int dbg_first = -1;  // first step whose pivot is not finite
+#endif
     // column 0 / pivot 0 / load row 0 for the first step
     if (tj == 0) {
       HMX_UNROLL
@@ -290,11 +297,84 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
         const int cur = k & 1, nxt = cur ^ 1;
         const double* colk = s_col + cur * NPAD;
         const double rinv = s_piv[cur], rinv2 = rinv * rinv;  // 1 / L_kk, 1 / pivot
+#ifdef HMX_DENSE_DEBUG
+        if (t_id == 0 && dbg_first < 0 && !(rinv == rinv && rinv < 1e300)) dbg_first = k;
+#endif
         double lj[R], li[R];  // L_jk L_kk (raw column) and L_ik / L_kk: their product is L_ik L_jk
         HMX_UNROLL
         for (int b = kb; b < R; ++b) lj[b] = colk[TG * b + tj];
         HMX_UNROLL
         for (int a = kb; a < R; ++a) li[a] = colk[TG * a + ti] * rinv2;
+        const int k1 = k + 1;
+        const bool in_kb = kt < TG - 1;  // column k1 lies in block kb, else in kb + 1
+#if HMX_DENSE_LOOKAHEAD == 1
+        // LOOK-AHEAD: the trailing update starts with the two block columns that can hold column k + 1 (b = kb and
+        // b = kb + 1: 2 R of the R (R + 1) / 2 FMA), then the owners of column k + 1 (tj == k1 mod TG) hand it, its pivot
+        // and the load row on to the next step, and the rest of the update (20k FMA per step at full size) runs while
+        // that hand-off (shared-memory stores, the rsqrt chain) is in flight: the dependent chain of a step is
+        // barrier -> column load -> 2 R FMA -> store + rsqrt  instead of the whole trailing update.
+        // Writing the `nxt` buffers this early is safe: they were `cur` of step k - 1, and every thread has passed the
+        // barrier that ended that step.  Control flow stays uniform (only the stores are predicated): a first version
+        // that updated column k + 1 inside `if (owner)` returned NaN pivots on the device at ptxas -O1 and above, finite
+        // ones at -O0 and in the CPU emulation (round-1 DESIGN.md 9.2, reproduced in round 2 with scripts/probe_dense.py).
+        HMX_UNROLL
+        for (int a = kb; a < R; ++a) {
+          if (tj > kt) A[a][kb] = fma(-li[a], lj[kb], A[a][kb]);
+          if (kb + 1 < R && a >= kb + 1) A[a][kb + 1 < R ? kb + 1 : kb] = fma(-li[a], lj[kb + 1 < R ? kb + 1 : kb], A[a][kb + 1 < R ? kb + 1 : kb]);
+        }
+        if (k1 < NDOF && tj == (k1 % TG)) {
+          double* coln = s_col + nxt * NPAD;
+          HMX_UNROLL
+          for (int a = kb; a < R; ++a) {
+            const double v = in_kb ? A[a][kb] : ((a >= kb + 1 && kb + 1 < R) ? A[a][kb + 1 < R ? kb + 1 : kb] : 0.0);
+            coln[TG * a + ti] = v;  // (entries above the diagonal are never used)
+          }
+          if (ti == tj) s_piv[nxt] = fast_rsqrt(in_kb ? A[kb][kb] : A[kb + 1 < R ? kb + 1 : kb][kb + 1 < R ? kb + 1 : kb]);
+        }
+        HMX_UNROLL
+        for (int a = kb + 2; a < R; ++a)
+          HMX_UNROLL
+          for (int b = kb + 2; b <= a; ++b) A[a][b] = fma(-li[a], lj[b], A[a][b]);
+#elif HMX_DENSE_LOOKAHEAD == 2
+        // KNOWN-BAD variant, kept only as the repro of the round-1 NaN (scripts/repro_dense_lookahead.py): the same
+        // look-ahead with column k + 1 updated INSIDE the owners' branch.  Every matrix entry receives exactly the same
+        // sequence of FMAs as in the variants above, the CPU emulation and `-Xptxas -O0` give finite, oracle-exact
+        // results -- at ptxas -O1 and above the device returns NaN pivots from a data-dependent, run-to-run
+        // reproducible step on (192 unknowns; 48- and 72-unknown cells are fine).  Not a race: an extra CTA barrier
+        // after the branch changes nothing.
+        const bool owner1 = k1 < NDOF && tj == (k1 % TG);
+        if (owner1) {
+          double* coln = s_col + nxt * NPAD;
+          if (in_kb) {
+            HMX_UNROLL
+            for (int a = kb; a < R; ++a) {
+              A[a][kb] = fma(-li[a], lj[kb], A[a][kb]);
+              coln[TG * a + ti] = A[a][kb];
+            }
+            if (ti == tj) s_piv[nxt] = fast_rsqrt(A[kb][kb]);
+          } else if (kb + 1 < R) {
+            HMX_UNROLL
+            for (int a = kb + 1; a < R; ++a) {
+              A[a][kb + 1 < R ? kb + 1 : kb] = fma(-li[a], lj[kb + 1 < R ? kb + 1 : kb], A[a][kb + 1 < R ? kb + 1 : kb]);
+              coln[TG * a + ti] = A[a][kb + 1 < R ? kb + 1 : kb];
+            }
+            coln[TG * kb + ti] = 0.0;
+            if (ti == tj) s_piv[nxt] = fast_rsqrt(A[kb + 1 < R ? kb + 1 : kb][kb + 1 < R ? kb + 1 : kb]);
+          }
+        }
+        HMX_UNROLL
+        for (int a = kb; a < R; ++a)
+          HMX_UNROLL
+          for (int b = kb; b <= a; ++b) {
+            if (b == kb) {
+              if (tj > kt && !(in_kb && owner1)) A[a][b] = fma(-li[a], lj[b], A[a][b]);
+            } else if (b == kb + 1) {
+              if (in_kb || !owner1) A[a][b] = fma(-li[a], lj[b], A[a][b]);
+            } else {
+              A[a][b] = fma(-li[a], lj[b], A[a][b]);
+            }
+          }
+#else
         // trailing update of the owned entries (i >= j > k)
         HMX_UNROLL
         for (int a = kb; a < R; ++a)
@@ -306,6 +386,7 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
               A[a][b] = fma(-li[a], lj[b], A[a][b]);
             }
           }
+#endif
         // forward substitution of the loads: y_p[k] = b_p[k] / L_kk, b_p[i] -= L_ik y_p[k]
         if (t_id > k && t_id < NDOF) {
           const double lrow = colk[t_id] * rinv2;
@@ -321,9 +402,8 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
           if (t_id == 0) s_dsave[k] = rinv;
         }
         // hand the next column, pivot and load row to the next step
-        const int k1 = k + 1;
         if (k1 < NDOF) {
-          const bool in_kb = kt < TG - 1;  // column k1 lies in block kb, else in kb + 1
+#if HMX_DENSE_LOOKAHEAD == 0
           if (tj == (k1 % TG)) {
             double* coln = s_col + nxt * NPAD;
             HMX_UNROLL
@@ -333,6 +413,7 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
             }
             if (ti == tj) s_piv[nxt] = fast_rsqrt(in_kb ? A[kb][kb] : A[kb + 1 < R ? kb + 1 : kb][kb + 1 < R ? kb + 1 : kb]);
           }
+#endif
           if (t_id == k1) {
             HMX_UNROLL
             for (int p = 0; p < NRHS; ++p) s_yb[nxt * NRHS + p] = brow[p];
@@ -404,7 +485,11 @@ HMX_DEV void elasticity_dense_cell_body(const CellParams& P) {
           HMX_UNROLL
           for (int i = 0; i < NB; ++i) s_cm[p * NB + i] = Cm[p][i];
       }
+#ifdef HMX_DENSE_DEBUG
+      if (P.iters != nullptr) P.iters[pt] = dbg_first;
+#else
       if (P.iters != nullptr) P.iters[pt] = 0;  // direct solve
+#endif
       if (P.resid != nullptr) P.resid[pt] = 0.0;
     }
     sync();
