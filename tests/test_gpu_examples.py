@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     ("hmm_3d.py", ["--macro", "4", "--micro", "8"]),
     ("diffusion_laminate.py", ["--macro", "8", "--micro", "32"]),
     ("elasticity_rotated_fibres.py", ["--macro", "4", "2", "2", "--micro", "8"]),
+    ("general_micro_mesh.py", ["--macro", "6", "--micro", "8"]),  # element-list kernel (not a reference example)
 ])  # fmt: skip
 def test_example_runs(script, args):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", script), *args], capture_output=True, text=True, timeout=600)
