@@ -70,16 +70,23 @@ struct ClusterLayout {
   using CS = CoarseSpace<CO, NM, NT, 0, 0, 0>;
   // two-level preconditioner: the semi-coarsened space along axis 0 (the z-slabs must not cut the summed axis and the
   // line sums run along the lanes of a warp)
-  // ... and the scratch of coarse_setup fits in the matrix area of one CTA (8^3 yes, 10^3 no: block Jacobi then)
-  static constexpr bool TWO = CS::GEOM && CS::SEMI && CS::SA == 0 && CS::NCD <= CS::MAXDOF &&
-                              CS::setup_doubles <= ((1 << D) - 1) * D * D * (NM / CL) * NM * NM + 4 * D * D * NM * NM;
+  // line sums by shuffles when a line of NM nodes x TPN lanes is an aligned power-of-two segment of a warp
+  static constexpr bool LSHFL = (TPN * NM) <= 32 && ((TPN * NM) & (TPN * NM - 1)) == 0;
+  // ... which is also a condition of the two-level method: with the generic line sums (NM barrier steps) and a 75-unknown
+  // coarse solve the 10^3 cell needs 152 instead of 379 iterations but pays 21.8 instead of 8.7 us for each -- 6.8k
+  // against 7.3k cell solves/s (measured; -DHMX_CLUSTER_TWO_ANY=1 builds it anyway: tests, experiments)
+#ifndef HMX_CLUSTER_TWO_ANY
+#define HMX_CLUSTER_TWO_ANY 0
+#endif
+  static constexpr bool TWO = CS::GEOM && CS::SEMI && CS::SA == 0 && CS::NCD <= CS::MAXDOF && (LSHFL || HMX_CLUSTER_TWO_ANY);
+  // the scratch of coarse_setup lives in the matrix area of the CTA when it fits (8^3), else in its global scratch
+  // (10^3: 243 KB; set-up only)
+  static constexpr bool SUG = TWO && CS::setup_doubles > ((1 << D) - 1) * D * D * (NM / CL) * NM * NM + 4 * D * D * NM * NM;
   static constexpr int NCD = TWO ? CS::NCD : 2;
   static constexpr int NTRI = TWO ? CS::NTRI : 0;
   static constexpr int NC2 = TWO ? CS::NC2 : 1;
   static constexpr int H = NM / 2;
   static constexpr int NBLK = (NCD + 31) / 32;
-  // line sums by shuffles when a line of NM nodes x TPN lanes is an aligned power-of-two segment of a warp
-  static constexpr bool LSHFL = (TPN * NM) <= 32 && ((TPN * NM) & (TPN * NM - 1)) == 0;
   static constexpr int NLINE = PZ * NM;  // x-lines this CTA owns
   static constexpr int NREC = ((NRHS * NCD + NRHS > NRHS * NRHS ? NRHS * NCD + NRHS : NRHS * NRHS) + 1) / 2 * 2;  // doubles a CTA sends per exchange
   static constexpr int EPART = NT / (NRHS * NRHS);  // node partitions of the epilogue's cross products
@@ -97,7 +104,10 @@ struct ClusterLayout {
                                    imax(imax(TWO ? CS::CBUF : 0, EPART * NRHS * NRHS), NRHS * NRHS + NV * (D + 1) * D + 2));
   static constexpr int o_work = o_u + NRHS * NCD;
   static constexpr int o_ei = ((o_work + WORK + 1) / 2) * 2;         // [NTRI] inverse coarse matrix, packed
-  static constexpr int o_p = ((o_ei + NTRI + 1) / 2) * 2;            // [NPB][NVEC]
+  // ... which moves to the global scratch (read through L1 by the coarse solve) when it is what pushes the CTA over
+  // 227 KB (10^3 on 5 CTAs: 22.8 KB)
+  static constexpr bool EIG = TWO && (o_ei + NTRI + 2 + NPB * NVEC + NH * NB * NOWN + 4 * NB * NPL) * 8 > 232448;
+  static constexpr int o_p = ((o_ei + (EIG ? 0 : NTRI) + 1) / 2) * 2;  // [NPB][NVEC]
   static constexpr int o_K = o_p + NPB * NVEC;                       // [NH][NB][NOWN]
   static constexpr int o_Kh = o_K + NH * NB * NOWN;                  // [4][NB][NPL]
   static constexpr int total = o_Kh + 4 * NB * NPL;
@@ -113,9 +123,12 @@ struct ClusterLayout {
   static_assert(2 * 27 * NOWN + 2 * 9 * 2 * NPL <= NH * NB * NOWN + 4 * NB * NPL, "diagonal partials must fit in the matrix area");
   static constexpr int PLANE_BYTES = NPL * NVEC * 8;
   static_assert(PLANE_BYTES % 16 == 0 && (o_p * 8) % 16 == 0 && HMX_MBAR_BYTES % 8 == 0, "bulk copies of whole node planes");
-  static_assert(!TWO || CS::setup_doubles <= NH * NB * NOWN + 4 * NB * NPL, "coarse set-up scratch must fit in the matrix area");
   static_assert(2 * NOWN * NVEC <= NH * NB * NOWN + 4 * NB * NPL, "epilogue copies of r~ and b~ must fit in the matrix area");
-  static constexpr int scratch_doubles = NOWN * NVEC + (ATG ? NA1 * T * NRC : 0);  // b~ of the own nodes (+ atoms), per CTA
+  // per-CTA global scratch: b~ of the own nodes (+ atoms, + inverse coarse matrix, + coarse set-up scratch)
+  static constexpr int g_atoms = NOWN * NVEC;
+  static constexpr int g_ei = g_atoms + (ATG ? NA1 * T * NRC : 0);
+  static constexpr int g_setup = ((g_ei + (EIG ? NTRI : 0) + 1) / 2) * 2;
+  static constexpr int scratch_doubles = g_setup + (SUG ? CS::setup_doubles : 0);
   static_assert(NM % CL == 0, "the cluster splits the cell into slabs of whole node planes");
   static_assert(TPN >= 1 && TPN <= 2 && NRHS % TPN == 0 && NT % 32 == 0 && NT >= NOWN * TPN && 32 % TPN == 0, "TPN threads per own node");
   static_assert(NT >= NRHS * NCD + NRHS && NT >= NRHS * NRHS, "one thread per coarse unknown and right-hand side in the exchanges");
@@ -249,12 +262,13 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   double* s_scal = sm + L::o_scal;
   double* s_u = sm + L::o_u;
   double* s_work = sm + L::o_work;
-  double* s_ei = sm + L::o_ei;
+  double* g_b = P.scratch + (size_t)bid() * L::scratch_doubles;
+  double* s_ei = L::EIG ? g_b + L::g_ei : sm + L::o_ei;
+  double* coarse_work = L::SUG ? g_b + L::g_setup : sm + L::o_K;
   double* s_p = sm + L::o_p;
   double* s_K = sm + L::o_K;
   double* s_Kh = sm + L::o_Kh;
-  double* g_b = P.scratch + (size_t)bid() * L::scratch_doubles;
-  double* s_atoms = L::ATG ? g_b + NOWN * NVEC : sm + L::o_atoms;
+  double* s_atoms = L::ATG ? g_b + L::g_atoms : sm + L::o_atoms;
   double* s_li = sm + L::o_li;  // [6][NPB] inverse Cholesky factors of the diagonal blocks (set-up only)
   double* s_lf = sm + L::o_lf;  // [6][NOWN] Cholesky factors of the own nodes (set-up only)
 
@@ -336,7 +350,7 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
     }
 
     // ---- 2. coarse matrix of this point, inverted (scratch: the matrix area) ----
-    if constexpr (TWO) coarse_setup<CS, CO, NM, NT>(pc, Ms, s_atoms, s_K, s_ei, s_work, s_red, NW * 8 / 2, red_flip);
+    if constexpr (TWO) coarse_setup<CS, CO, NM, NT>(pc, Ms, s_atoms, coarse_work, s_ei, s_work, s_red, NW * 8 / 2, red_flip);
 
     // ---- 3. diagonal blocks: the two halves of the simplex types in parallel (warp-uniform when NOWN is a multiple
     //         of 32), partial sums through the matrix area ----

@@ -199,17 +199,15 @@ def cluster_tpn():
 
 def cluster_coarse_dofs(prog, n, cl, threads=512):
     """Unknowns of the cluster kernel's coarse space (mirrors ``ClusterLayout::TWO`` in csrc/hmx_cell_cluster.cuh): the
-    level-1 space summed along micro axis 0 when the coefficient does not depend on it and the set-up scratch fits in
-    one CTA's share of the matrix area; 0 = block Jacobi only."""
+    level-1 space summed along micro axis 0 when the coefficient does not depend on it; 0 = block Jacobi only."""
     if os.environ.get("HMX_PRECOND", "twolevel") == "jacobi" or n % 2 or n < 4 or threads // 6 < 32:
         return 0
     h = n // 2
     if 3 * h**3 <= 96 or (prog.ydep & 1) or 3 * h * h > 96:
         return 0
-    ndep = bin(prog.ydep & 7).count("1")
-    setup = 27 * 3 * 3 * h**3 + max(1, prog.natoms) * 6 * h**ndep
-    if setup > 63 * (n // cl) * n * n + 36 * n * n:
-        return 0
+    lanes = cluster_tpn() * n  # line sums by warp shuffles: an x-line is an aligned power-of-two segment of a warp
+    if (lanes > 32 or lanes & (lanes - 1)) and "-DHMX_CLUSTER_TWO_ANY=1" not in _extra_flags():
+        return 0  # (10^3: measured slower than block Jacobi with the generic line sums, csrc/hmx_cell_cluster.cuh)
     return 3 * h * h
 
 
@@ -236,6 +234,8 @@ def cluster_smem_bytes(prog, n, cl):
     work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36, 110)
     ntri = ncd * (ncd + 1) // 2 if two else 0
     doubles = 4 + (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
+    if two and 8 * doubles > SMEM_LIMIT:  # the inverse coarse matrix moves to the global scratch (ClusterLayout::EIG)
+        doubles -= ntri
     return 8 * doubles
 
 

@@ -75,6 +75,26 @@ def test_emulated_cluster_kernel_two_level_matches_golden_vectors():
     assert it.max() < 230  # (block Jacobi alone needs ~ 400 at this tolerance)
 
 
+def test_emulated_cluster_kernel_two_level_on_a_10_cube_cell(monkeypatch):
+    """-DHMX_CLUSTER_TWO_ANY=1: the two-level method where an x-line is not a power-of-two warp segment (generic line
+    sums), with the coarse set-up scratch and the inverse coarse matrix in the global scratch (ClusterLayout::SUG / EIG):
+    5 CTAs per cluster, 75 coarse unknowns.  Not the default at 10^3 (measured slower than block Jacobi there)."""
+    import emu
+
+    monkeypatch.setenv("HMX_EXTRA_NVCC", "-DHMX_CLUSTER_TWO_ANY=1")
+    case = K.BY_NAME["e3_fibre_rot_n10_l2"]
+    prog = K.program(case)
+    assert native.cluster_size(prog, 10) == 5 and native.cluster_coarse_dofs(prog, 10, 5) == 75
+    qp, qw = K.tables(case, prog)
+    x = K.points(case, 1)
+    s = emu.EmuSolver(prog, case.n, qp, qw, rtol=1e-9, variant=native.CLUSTER, grid=5)
+    assert s.info[0] <= native.SMEM_LIMIT and abs(s.info[0] - native.cluster_smem_bytes(prog, 10, 5)) <= 64
+    A, it, res = s.cell_tensors(x, return_stats=True)
+    ref = K.oracle_tensor(case, K.oracle_cell(case, prog), x[0])
+    assert np.abs(A[0] - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert it[0] < 260  # (block Jacobi: ~ 480)
+
+
 def test_emulated_cluster_kernel_correctors_and_local_matrix():
     import emu
 
