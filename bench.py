@@ -333,7 +333,8 @@ def run_ours(args, rank, world, local_rank):
                      ("c4", True, "pcg", "weak"), ("c3", True, "auto", "weak"), ("c2", True, "auto", "weak"),
                      # the cluster-resident assembled stencil (csrc/hmx_cell_cluster.cuh): opt-in on the 8^3 cell, the
                      # default where the cell exceeds one SM (10^3), next to the matrix-free kernel on the same cell
-                     ("c4", False, "cluster", "weak"), ("c4n10", False, "auto", "weak"), ("c4n10", False, "pcg", "weak")]  # fmt: skip
+                     ("c4", False, "cluster", "weak"), ("c4n10", False, "auto", "weak"), ("c4n10", False, "pcg", "weak"),
+                     ("c4s", False, "pcg", "weak")]  # fmt: skip
         for name, collapse, how, scaling in todo:
             if name == args.workload and not collapse and scaling == SCALING and how == "auto":
                 continue

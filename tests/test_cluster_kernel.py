@@ -41,6 +41,15 @@ def test_host_side_sizing_mirrors_the_kernel_layout():
     assert native.cluster_size(prog, 10) == 5 and native.cluster_coarse_dofs(prog, 10, 5) == 0
     with pytest.raises(native.HmxError):
         native.resolve(K.program(K.BY_NAME["p3_smooth_n4"]), 4, variant=native.CLUSTER)
+    # default choice: cells that exceed one SM, and 8^3 cells whose coefficient varies along all three axes (no coarse
+    # space fits either kernel: the cheaper operator wins); the fibre cell (two-level matrix-free kernel) stays
+    from hommx_b200 import codegen, workloads
+    from hommx_b200 import ufl as pufl
+
+    A, Dt = workloads.coefficient("c4s", pufl)
+    ball = codegen.build_program(A, 3, 1, Dt)
+    assert native.default_variant(ball, 8) == native.CLUSTER and native.default_variant(ball, 6) == native.MATRIX_FREE
+    assert native.default_variant(prog, 8) == native.MATRIX_FREE and native.default_variant(prog, 10) == native.CLUSTER
 
 
 @pytest.mark.parametrize("name", ["e3_fibre_rot_n4", "e3_cubic_shear_n4"])
