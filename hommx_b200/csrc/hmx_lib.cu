@@ -66,6 +66,27 @@ __global__ void __launch_bounds__(256) hmx_lift(long long n, const long long* __
     b[i] = fixed ? ubc[i] : b[i] - acc;
   }
 }
+// Macro element matrices from homogenised tensors at SEVERAL macro quadrature points per cell (a higher-order macro
+// rule; the reference evaluates the barycentre only, hmm.py:349-352):  S_loc = |T| C^T (sum_q w_q A_hom(x_q)) C  --
+// the P1 macro gradients / strains C are constant per cell, so the rule acts on the tensor alone.  One thread per entry.
+template <int D, int KIND>
+__global__ void __launch_bounds__(256) hmx_macro_elements(long long n_cells, const int* __restrict__ cell_nodes,
+                                                          const double* __restrict__ node_xyz, int nq,
+                                                          const double* __restrict__ wq, const double* __restrict__ A_pts,
+                                                          double* __restrict__ S_loc) {
+  constexpr int MV = KIND == 0 ? D : D * (D + 1) / 2, NB = KIND == 0 ? D + 1 : (D + 1) * D;
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n_cells; c += (long long)gridDim.x * blockDim.x) {
+    double verts[(D + 1) * 3], Ah[MV * MV];
+    for (int v = 0; v <= D; ++v)
+      for (int k = 0; k < 3; ++k) verts[v * 3 + k] = node_xyz[(long long)cell_nodes[c * (D + 1) + v] * 3 + k];
+    for (int e = 0; e < MV * MV; ++e) {
+      double a = 0.0;
+      for (int q = 0; q < nq; ++q) a += wq[q] * A_pts[(c * nq + q) * MV * MV + e];  // fixed order
+      Ah[e] = a;
+    }
+    hmx::macro_element_matrix<D, KIND>(verts, Ah, S_loc + c * NB * NB);
+  }
+}
 // Jacobi-PCG building blocks.  Scalars live in a small device array sc[]: 0 rz, 3 rz0; every dot product is reduced in
 // two FIXED-ORDER stages (block partials bp[blockIdx.x], then the same sum of the partials in every consumer block), so
 // the macro solve is bitwise reproducible like the assembly that feeds it (no floating-point atomics).
@@ -823,6 +844,30 @@ int hmx_halo_sum_dev(hmx_t* h, void* nccl_comm, double* csr_vals, const int64_t*
     hmx_halo_unpack<<<grid_1d(n, 256, h->info[6]), 256, 0, h->stream>>>(n, (const long long*)slots, csr_vals, buf);
     HMX_CUDA(h, cudaGetLastError());
   }
+  return HMX_OK;
+}
+
+int hmx_macro_elements_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, const double* node_xyz, int32_t nq,
+                           const double* weights, const double* A_pts, double* S_loc) {
+  if (!h) return HMX_ERR_ARG;
+  if (n_cells < 0 || nq < 1 || !weights || (n_cells > 0 && (!cell_nodes || !node_xyz || !A_pts || !S_loc)))
+    return fail(h, HMX_ERR_ARG, "hmx_macro_elements: null buffer or empty rule");
+  if (n_cells == 0) return HMX_OK;
+  DeviceGuard guard(h->device);
+  HMX_CUDA(h, guard.status);
+  HMX_CUDA(h, h->l_qw.reserve((size_t)nq * sizeof(double)));
+  HMX_CUDA(h, cudaMemcpyAsync(h->l_qw.p, weights, (size_t)nq * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int g = grid_1d(n_cells, 256, h->info[6]);
+  const double* wq = h->l_qw.as<double>();
+  if (h->dim == 2 && h->kind == HMX_POISSON)
+    hmx_macro_elements<2, 0><<<g, 256, 0, h->stream>>>(n_cells, cell_nodes, node_xyz, nq, wq, A_pts, S_loc);
+  else if (h->dim == 3 && h->kind == HMX_POISSON)
+    hmx_macro_elements<3, 0><<<g, 256, 0, h->stream>>>(n_cells, cell_nodes, node_xyz, nq, wq, A_pts, S_loc);
+  else if (h->dim == 2)
+    hmx_macro_elements<2, 1><<<g, 256, 0, h->stream>>>(n_cells, cell_nodes, node_xyz, nq, wq, A_pts, S_loc);
+  else
+    hmx_macro_elements<3, 1><<<g, 256, 0, h->stream>>>(n_cells, cell_nodes, node_xyz, nq, wq, A_pts, S_loc);
+  HMX_CUDA(h, cudaGetLastError());
   return HMX_OK;
 }
 

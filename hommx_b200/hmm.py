@@ -89,6 +89,7 @@ class BaseHMM:
         shard=True,
         collapse_invariant_axes=True,
         cell_solver="auto",
+        macro_quadrature_degree=None,
     ):
         self._logger = logging.getLogger(__name__)
         self._msh = as_simplex_mesh(msh)
@@ -165,6 +166,10 @@ class BaseHMM:
         # exact symmetry reduction: micro axes the coefficient does not depend on are solved on one layer of
         # cubes (csrc/hmx_cell_common.cuh, Grid<.., COLL>); False solves the full n^d cell
         self._collapse = bool(collapse_invariant_axes)
+        # macro quadrature: None / 0 / 1 = the barycentre of every macro cell, as the reference (hmm.py:349-352); k >= 2 =
+        # the simplex rule of degree k: the cell problem is solved at every rule point and S_loc = |T| C^T (sum_q w_q
+        # A_hom(x_q)) C (hmx_macro_elements_dev)
+        self._macro_qdeg = int(macro_quadrature_degree or 0)
         # "pcg": the matrix-free PCG kernels; "direct": dense Cholesky per cell (elasticity cells of <= 192 unknowns,
         # csrc/hmx_cell_dense.cuh); "cluster": PCG on the assembled stencil resident in a thread-block cluster's
         # distributed shared memory (3-D elasticity, full cells; csrc/hmx_cell_cluster.cuh); "auto": direct where the
@@ -291,9 +296,12 @@ class BaseHMM:
             self._solver.set_stream(torch.cuda.current_stream().cuda_stream)
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-            self._solver.assemble_macro_dev(
-                d["hi"] - d["lo"], d["cells"], d["n_nodes"], d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"],
-            )  # fmt: skip
+            if self._macro_qdeg >= 2:
+                self._cells_at_rule_points(d)
+            else:
+                self._solver.assemble_macro_dev(
+                    d["hi"] - d["lo"], d["cells"], d["n_nodes"], d["xyz"], 0, None, None, None, d["S"], d["it"], d["res"],
+                )  # fmt: skip
             ev[1].record()
             self._solver.gather_csr_dev(d["nnz"], d["ptr"], d["src"], d["S"], d["vals"])
             ev[2].record()
@@ -323,6 +331,29 @@ class BaseHMM:
             self._A_values = self._full_values()
         self._A = sp.csr_matrix((self._A_values, self._pattern.indices, self._pattern.indptr), shape=(self._num_global_dofs,) * 2)
         self._needs_reassembly = False
+
+    def _cells_at_rule_points(self, d):
+        """Higher-order macro quadrature: A_hom at the points of the degree-k simplex rule in every local macro cell
+        (one launch of the cell kernel over n_cells * nq points), then the element matrices from their weighted mean."""
+        import torch
+
+        n = d["hi"] - d["lo"]
+        if "rule" not in d:
+            pts, wts = quadrature.default_rule(self._tdim, self._macro_qdeg)
+            lam = np.concatenate([1.0 - pts.sum(axis=1, keepdims=True), pts], axis=1)  # barycentric coordinates (nq, d+1)
+            d["rule_w"] = np.ascontiguousarray(wts / wts.sum())
+            d["rule"] = torch.as_tensor(lam, device=d["xyz"].device)
+            nq, m = len(wts), self._solver.m
+            d["A_pts"] = torch.empty((n, nq, m, m), dtype=torch.float64, device=d["xyz"].device)
+            d["it_pts"] = torch.empty(n * nq, dtype=torch.int32, device=d["xyz"].device)
+            d["res_pts"] = torch.empty(n * nq, dtype=torch.float64, device=d["xyz"].device)
+        nq = d["rule"].shape[0]
+        verts = d["xyz"][d["cells"].long()]  # (n, d+1, 3)
+        x = torch.einsum("qa,eak->eqk", d["rule"], verts).reshape(n * nq, 3).contiguous()  # mapped rule points
+        self._solver.cell_tensors_dev(n * nq, x, d["A_pts"], d["it_pts"], d["res_pts"])
+        self._solver.macro_elements_dev(n, d["cells"], d["xyz"], d["rule_w"], d["A_pts"], d["S"])
+        d["it"].copy_(d["it_pts"].view(n, nq).max(dim=1).values)
+        d["res"].copy_(d["res_pts"].view(n, nq).max(dim=1).values)
 
     def _halo_sum(self):
         """Sum of the value slots shared between ranks: the only collective of the path.  The exchange buffer lists
@@ -356,7 +387,8 @@ class BaseHMM:
         return v.cpu().numpy()
 
     def _compute_local_stiffness(self, local_cell_index):
-        """One macro cell (the finer seam, hmm.py:334-369): returns the (n_b, n_b) local matrix."""
+        """One macro cell (the finer seam, hmm.py:334-369): returns the (n_b, n_b) local matrix (barycentre rule, as
+        the reference; the macro_quadrature_degree option acts in _assemble_stiffness)."""
         self._ensure_solver()
         nb = self._num_basis_functions_per_cell
         cells = np.ascontiguousarray(self._msh.cells[local_cell_index : local_cell_index + 1], dtype=np.int32)

@@ -31,7 +31,7 @@ _HEADERS = ("hmx_platform.cuh", "hmx_cell_common.cuh", "hmx_cell_poisson.cuh", "
 MATRIX_FREE, DENSE, CLUSTER, ELEMENT_LIST = 0, 3, 4, 5  # (1, 2: the slower assembled-operator experiments, experiments/)
 DENSE_MAX_DOF = 192  # register tile of the dense Cholesky kernel: 12 x 12 blocks of 16 x 16 threads
 SMEM_LIMIT = 227 * 1024
-ABI_VERSION = 7  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
+ABI_VERSION = 8  # HMX_ABI_VERSION of include/hmx.h these bindings were written for
 
 
 class HmxError(RuntimeError):
@@ -117,6 +117,7 @@ SYMBOLS = {
     "hmx_halo_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_unpack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hmx_halo_sum_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hmx_macro_elements_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmx_macro_load_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "hmx_macro_lift_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -636,6 +637,13 @@ class CellSolver:
         """pack + ncclAllReduce + unpack on the handle's stream; ``nccl_comm`` is a raw ncclComm_t (an int address)."""
         dp = self._dp
         self._check(self.lib.hmx_halo_sum_dev(self._h, C.c_void_p(int(nccl_comm)), dp(csr_vals), dp(slots), int(n), dp(buf)))
+
+    def macro_elements_dev(self, n_cells, cell_nodes, node_xyz, weights, A_pts, S_loc):
+        """S_loc of every macro cell from tensors at ``len(weights)`` macro quadrature points per cell."""
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        dp = self._dp
+        self._check(self.lib.hmx_macro_elements_dev(self._h, int(n_cells), dp(cell_nodes), dp(node_xyz), len(w), _ptr(w),
+                                                    dp(A_pts), dp(S_loc)))  # fmt: skip
 
     def macro_load_dev(self, image, n_cells, cell_nodes, node_xyz, qp, qw, Fe):
         """Element load vectors Fe [n_cells][(dim+1)*bs] of the right-hand side compiled into ``image``."""

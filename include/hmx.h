@@ -31,7 +31,7 @@ typedef struct hmx_handle hmx_t;
 /* Bumped whenever a signature, the layout of hmx_desc or the kernel-image contract (hmx_info, CellParams) changes;
  * a binding checks it against the value it was written for before calling anything else (a stale libhmx.so next
  * to new Python sources would otherwise be called with the wrong arguments). */
-#define HMX_ABI_VERSION 7
+#define HMX_ABI_VERSION 8
 int32_t hmx_abi_version(void);
 
 enum hmx_status {
@@ -163,6 +163,14 @@ int hmx_halo_unpack_dev(hmx_t* h, double* csr_vals, const int64_t* slots, int64_
  * list is global: slots touched by more than one rank, in the same order everywhere).  All pointers are device
  * pointers. */
 int hmx_halo_sum_dev(hmx_t* h, void* nccl_comm, double* csr_vals, const int64_t* slots, int64_t n, double* buf);
+
+/* SURVEY 8f row 4, "higher-order macro quadrature": macro element matrices from homogenised tensors at nq macro
+ * quadrature points per cell,  S_loc = |T| C^T (sum_q weights[q] A_pts[cell][q]) C  (the reference evaluates the cell
+ * problem at the barycentre only, hmm.py:349-352; with P1 macro elements C is constant per cell, so a higher-order rule
+ * acts on the tensor alone).  A_pts [n_cells][nq][m][m] comes from hmx_cell_tensors_dev at the mapped points; weights
+ * [nq] (HOST, sum 1); S_loc [n_cells][n_b][n_b] then goes through hmx_gather_csr_dev as usual.  Device pointers. */
+int hmx_macro_elements_dev(hmx_t* h, int64_t n_cells, const int32_t* cell_nodes, const double* node_xyz, int32_t nq,
+                           const double* weights, const double* A_pts, double* S_loc);
 
 /* the macro load vector on the device.  Replaces the FFCx kernel behind
  * `_assemble_vector_array(b_local.array_w, self._L, ...)` (hmm.py:445-450; L = inner(f(x), v) dx, hmm.py:131-133).

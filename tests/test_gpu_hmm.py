@@ -262,3 +262,46 @@ def test_device_load_vector_matches_host_assembly(dim, bs):
     s.set_right_hand_side(lambda x: 2.0 if bs == 1 else pufl.as_vector([1.0, 0.0, 0.0]))  # a new f loads a new module
     b2 = s._assemble_load_device().cpu().numpy()
     assert np.abs(b2 - fem.assemble_load(s._V_macro, s._f)).max() <= 1e-13 * np.abs(b2).max()
+
+
+@pytest.mark.parametrize("kind", ["poisson", "elasticity"])
+def test_higher_order_macro_quadrature(kind):
+    """SURVEY 8f row 4 (second half): macro_quadrature_degree=k solves the cell problem at every point of the degree-k
+    simplex rule and assembles S_loc = |T| C^T (sum_q w_q A_hom(x_q)) C (hmx_macro_elements_dev).  Checked against the
+    oracle's tensors at the same points; degree 1 / None is the reference's barycentre rule."""
+    from hommx_b200 import quadrature
+    from oracle import hmm_oracle as ho
+
+    if kind == "poisson":
+        m, mic, n = mesh.create_rectangle((0.0, 0.0), (1.0, 0.8), (3, 2)), mesh.create_unit_square(8, 8), 8
+        A, An = Cf.analytic2(pufl), Cf.analytic2(npufl)  # 0.33 + 0.15 (sin 2 pi x0 + sin 2 pi y0): nonlinear in x
+        mk = lambda **kw: PoissonHMM(m, A, lambda x: 1.0, mic, 0.1, petsc_options_cell_problem=TIGHT, **kw)  # noqa: E731
+        omic = ho.MicroCell(mic, "poisson", 4)
+    else:
+        m, mic, n = mesh.create_box((0.0, 0.0, 0.0), (1.0, 0.5, 0.25), (2, 1, 1)), mesh.create_unit_cube(4, 4, 4), 4
+        A, An = Cf.hooke_smooth_3d(pufl), Cf.hooke_smooth_3d(npufl)
+        mk = lambda **kw: LinearElasticityHMM(m, A, lambda x: pufl.as_vector([0.0, 0.0, -1.0]), mic, 0.1,
+                                              petsc_options_cell_problem=TIGHT, **kw)  # noqa: E731
+        omic = None
+    base, hi = mk(), mk(macro_quadrature_degree=3)
+    base._assemble_stiffness()
+    hi._assemble_stiffness()
+    d = m.dim
+    pts, wts = quadrature.default_rule(d, 3)
+    lam = np.concatenate([1.0 - pts.sum(axis=1, keepdims=True), pts], axis=1)
+    wts = wts / wts.sum()
+    S = hi._dev["S"].cpu().numpy().reshape(m.num_cells, hi._num_basis_functions_per_cell, -1)
+    for c in (0, m.num_cells - 1):
+        verts = m.x[m.cells[c]]
+        xq = lam @ verts
+        if omic is not None:
+            Aq = np.array([ho.cell_tensor(omic, An, x) for x in xq])
+        else:
+            Aq = hi.cell_tensors(xq)  # (elasticity: the kernel's own tensors, pinned against the oracle elsewhere)
+        ref = ho.local_stiffness_from_tensor(np.einsum("q,qij->ij", wts, Aq), verts, kind)
+        assert np.abs(S[c] - ref).max() <= 1e-9 * np.abs(ref).max()
+    # the rule matters for a coefficient that is nonlinear in x, and the barycentre default is untouched
+    if kind == "poisson":
+        assert np.abs(hi._A_values - base._A_values).max() > 1e-4 * np.abs(base._A_values).max()
+    u = hi.solve()
+    assert np.isfinite(u.x.array).all()
