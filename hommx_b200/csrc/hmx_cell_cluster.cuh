@@ -34,9 +34,12 @@
 // M^-1 = blockdiag(K)^-1 + P E^-1 P^T (hmx_cell_coarse.cuh) iterate by iterate.  Every thread keeps the L of its node.
 //
 // Cluster-wide reductions (p.Kp; r~.r~ together with the restricted residual P^T r): warp shuffles -> CTA partial
-// -> every CTA stores its partial into every CTA's receive buffer (DSMEM) -> barrier.cluster -> every CTA adds the
-// partials in rank order: all CTAs hold bit-identical scalars and take identical branches.  Two cluster barriers per
-// iteration (they also order the reuse of the halo planes and receive buffers).  r.z needs no second reduction: r~.z~ = r~.r~ + (P^T r).E^-1 (P^T r).
+// -> every CTA stores its partial into every CTA's receive buffer (st.async: DSMEM stores counted as transaction
+// bytes on the RECEIVER's mbarrier) -> every CTA waits on its own mbarrier and adds the partials in rank order: all
+// CTAs hold bit-identical scalars and take identical branches.  No barrier.cluster inside the iteration (its
+// release is a MEMBAR.ALL.GPU, its acquire a CCTL.IVALL): the two exchanges alternate, and a CTA can only send round
+// k + 1 of one after it has received round k of the other from every peer, which also orders the reuse of the halo
+// planes and receive buffers.  r.z needs no second reduction: r~.z~ = r~.r~ + (P^T r).E^-1 (P^T r).
 // Coarse space: the semi-coarsened space of hmx_cell_coarse.cuh (level-1 Kuhn P1 summed along the first micro axis
 // when the coefficient does not depend on it), set up by the same coarse_setup in every CTA; restriction = line sums
 // along x (warp shuffles) followed by the 2-D Kuhn restriction of the lines a CTA owns.
@@ -92,8 +95,8 @@ struct ClusterLayout {
   static constexpr int EPART = NT / (NRHS * NRHS);  // node partitions of the epilogue's cross products
   HMX_HOSTDEV static constexpr int imax(int a, int b) { return a > b ? a : b; }
   // ---- shared memory (doubles) ----
-  static constexpr int o_bar = 0;                                    // mbarrier of the halo planes (HMX_MBAR_BYTES)
-  static constexpr int o_red = o_bar + HMX_MBAR_BYTES / 8;           // [NW][8] warp partials
+  static constexpr int o_bar = 0;                                    // 3 mbarriers: halo planes, p.Kp exchange, residual exchange
+  static constexpr int o_red = o_bar + 3 * HMX_MBAR_BYTES / 8;       // [NW][8] warp partials
   static constexpr int o_xch = o_red + NW * 8;                       // [CL][8] p.Kp partials of every CTA
   static constexpr int o_recv = o_xch + CL * 8;                      // [CL][NREC] restricted residual + r~.r~ partials
   static constexpr int o_scal = o_recv + CL * NREC;                  // [8] r~.r~ of every right-hand side
@@ -255,7 +258,9 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   constexpr int NPC1 = CO::NPC > 0 ? CO::NPC : 1;
 
   double* sm = dyn_smem();
-  MBar* s_bar = reinterpret_cast<MBar*>(sm + L::o_bar);
+  MBar* s_bar = reinterpret_cast<MBar*>(sm + L::o_bar);  // halo planes (bulk copies of the neighbours)
+  MBar* s_bar_x = reinterpret_cast<MBar*>(sm + L::o_bar + HMX_MBAR_BYTES / 8);      // p.Kp partials of all CTAs
+  MBar* s_bar_c = reinterpret_cast<MBar*>(sm + L::o_bar + 2 * HMX_MBAR_BYTES / 8);  // restricted residual + r~.r~ partials
   double* s_red = sm + L::o_red;
   double* s_xch = sm + L::o_xch;
   double* s_recv = sm + L::o_recv;
@@ -288,13 +293,15 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
   const double vol = hh * hh * hh / 6.0;
   const double sqrtw = sqrt(vol);
   int red_flip = 0;
-  unsigned halo_parity = 0;
+  unsigned halo_parity = 0, x_parity = 0, c_parity = 0;
   // offset of direction mask m (bits x, y, z) from node slot s of the p buffer, forwards / backwards
   auto fwd = [&](int m) { return ((m & 1) ? oxp : 0) + ((m & 2) ? oyp : 0) + ((m & 4) ? NPL : 0); };
   auto bwd = [&](int m) { return ((m & 1) ? oxm : 0) + ((m & 2) ? oym : 0) - ((m & 4) ? NPL : 0); };
 
   if (t_id == 0) {
     mbar_init(s_bar, 1);
+    mbar_init(s_bar_x, 1);
+    mbar_init(s_bar_c, 1);
     mbar_fence_init();
   }
   cluster_sync();  // every CTA's mbarrier exists before a peer's copy can signal it
@@ -613,12 +620,18 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
           send = true;
           slot = NRHS * NCD + q;
         }
+        // every value goes to every CTA (this one included) as a store counted on the receiver's mbarrier: the wait
+        // below needs no cluster barrier (whose release is a MEMBAR.ALL.GPU and whose acquire invalidates L1).  One
+        // buffer per exchange suffices: a CTA sends round k + 1 only after it has received round k of the OTHER
+        // exchange from every peer, which the peer sent after it had read this buffer's round k.
         if (send) {
           HMX_UNROLL
-          for (int rk = 0; rk < CL; ++rk) cluster_map(s_recv, rk)[rank * NREC + slot] = v;
+          for (int rk = 0; rk < CL; ++rk) st_async_f64(s_recv + rank * NREC + slot, v, s_bar_c, rk);
         }
+        if (t_id == 0) mbar_arrive_expect_tx(s_bar_c, (unsigned)(CL * ((TWO ? NRHS * NCD : 0) + NRHS) * 8));
       }
-      cluster_sync();
+      mbar_wait(s_bar_c, c_parity);
+      c_parity ^= 1u;
       // totals in rank order: bit-identical in every CTA
       if (TWO && t_id < NRHS * NCD) {
         double v = 0.0;
@@ -779,9 +792,11 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
           double v = 0.0;
           for (int w = 0; w < NW; ++w) v += s_red[w * 8 + t_id];
           HMX_UNROLL
-          for (int rk = 0; rk < CL; ++rk) cluster_map(s_xch, rk)[rank * 8 + t_id] = v;
+          for (int rk = 0; rk < CL; ++rk) st_async_f64(s_xch + rank * 8 + t_id, v, s_bar_x, rk);
         }
-        cluster_sync();
+        if (t_id == 0) mbar_arrive_expect_tx(s_bar_x, (unsigned)(CL * NRHS * 8));
+        mbar_wait(s_bar_x, x_parity);
+        x_parity ^= 1u;
       }
       HMX_UNROLL
       for (int q = 0; q < NRL; ++q) {

@@ -167,6 +167,14 @@ HMX_DEV void bulk_s2c(void* dst, const void* src, unsigned bytes, MBar* bar, int
                "r"(smem_u32(src)), "r"(bytes), "r"(cluster_map_u32(bar, rank))
                : "memory");
 }
+// one 8-byte store into the shared memory of CTA `rank` that is COUNTED on that CTA's mbarrier (st.async ...
+// mbarrier::complete_tx::bytes): the receiver waits on its own mbarrier for the expected number of bytes -- no fence, no
+// cluster barrier, no L1 invalidation on either side.  dst / bar: addresses of the same objects in THIS CTA.
+HMX_DEV void st_async_f64(double* dst, double v, MBar* bar, int rank) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(cluster_map_u32(dst, rank)),
+               "l"(__double_as_longlong(v)), "r"(cluster_map_u32(bar, rank))
+               : "memory");
+}
 HMX_DEV void atomic_add_u64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }  // RED.E.ADD.64
 // busy-wait for about `cycles` SM clocks (CS2R on the clock register): staggers the right-hand-side groups of a CTA
 HMX_DEV void spin_cycles(long long cycles) {

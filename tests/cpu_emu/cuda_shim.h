@@ -196,6 +196,12 @@ inline void bulk_s2c(void* dst, const void* src, unsigned bytes, MBar* bar, int 
   rb->tx -= bytes;
   mbar_maybe_complete(rb);
 }
+inline void st_async_f64(double* dst, double v, MBar* bar, int rank) {
+  *cluster_map(dst, rank) = v;
+  MBar* rb = cluster_map(bar, rank);
+  rb->tx -= 8;
+  mbar_maybe_complete(rb);
+}
 inline void atomic_add_u64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline void spin_cycles(long long) {}  // timing only: nothing to emulate
 }  // namespace hmx
