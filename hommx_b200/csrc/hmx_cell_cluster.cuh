@@ -690,7 +690,9 @@ HMX_DEV void elasticity_cluster_cell_body(const CellParams& P) {
     };
 
     // the search direction of this thread lives in its own slot of s_p only (no register copy: the slot is rewritten
-    // after the two cluster barriers that follow the products reading it)
+    // after the CTA barrier of the p.Kp reduction, which every local reader passes after its products; the copy
+    // engine has read the boundary planes by then too -- the neighbour's p.Kp partial, which the exchange waits
+    // for, was sent after that neighbour had waited for the copy)
     double* p_own = s_p + (size_t)pb * NVEC + h * NVL;
     double rz[NRL], tol2[NRL];
     bool active[NRL];

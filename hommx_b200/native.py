@@ -179,9 +179,9 @@ def default_variant(prog, n, collapse=False):
         return DENSE
     # cells that exceed one SM (3-D, n >= 10: the matrix-free kernel would keep its vectors in L2): the assembled
     # stencil resident in the distributed shared memory of a thread-block cluster, where a portable cluster (<= 8
-    # CTAs) holds it (measured on B200, 10^3 fibre cell: 7.8k against 5.8k cell solves/s; profiles/r02_cluster.md)
+    # CTAs) holds it (measured on B200, 10^3 fibre cell: 7.9k against 5.2k-5.8k cell solves/s; profiles/r02_cluster.md)
     # ... and 8^3 cells whose coefficient varies along all three micro axes: no coarse space fits either kernel there
-    # (block Jacobi, ~370 iterations for a stiff ball), and the cheaper operator wins (32.2k against 29.2k cell solves/s)
+    # (block Jacobi, ~370 iterations for a stiff ball), and the cheaper operator wins (34.9k against 29.3k cell solves/s)
     if prog.dim == 3 and coll == 0 and os.environ.get("HMX_ELASTICITY_VARIANT") != "matrix-free":
         big = vectors_in_l2(prog, n, 0)
         no_coarse = n >= 8 and n % 2 == 0 and coarse_dofs(prog, n, MATRIX_FREE, 0) == 0 and precond_mode(prog, MATRIX_FREE) == 1
