@@ -249,14 +249,54 @@ struct AtomIdx {
 // Sum NV values per thread over the CTA; every thread ends with the same totals (fixed
 // summation order -> deterministic).  One BAR.SYNC.  `buf` holds NW*NV doubles; callers
 // alternate between two buffers so that no trailing barrier is needed.
+// Warp sums of NV values at once with a TRANSPOSING butterfly: while a lane still holds more than one value it keeps
+// one half of them (which half: its lane bit of the step) and hands the other half to its partner, so every step
+// moves half as many values as the one before; the steps that are left sum the single remaining value.
+// P - 1 + 5 - log2(P) shuffles (P = NV rounded up to a power of two) instead of 5 NV: 6 instead of 15 for NV = 3, 31
+// instead of 90 for NV = 18.  The total of value warp_multi_index<NV>(lane) is returned (every lane of the warp calls).
+template <int NV>
+struct WarpMulti {
+  static_assert(NV >= 1 && NV <= 32, "at most one value per lane");
+  static constexpr int P = NV <= 1 ? 1 : NV <= 2 ? 2 : NV <= 4 ? 4 : NV <= 8 ? 8 : NV <= 16 ? 16 : 32;
+};
+template <int NV>
+HMX_DEV int warp_multi_index(int lane) {
+  int k = 0;
+  HMX_UNROLL
+  for (int st = 0; st < 5; ++st)
+    if ((WarpMulti<NV>::P >> st) > 1 && (lane & (16 >> st))) k += WarpMulti<NV>::P >> (st + 1);
+  return k;
+}
+template <int NV>
+HMX_DEV double warp_sum_multi(const double (&v)[NV], int lane) {
+  constexpr int P = WarpMulti<NV>::P;
+  double w[P];
+  HMX_UNROLL
+  for (int k = 0; k < P; ++k) w[k] = k < NV ? v[k < NV ? k : 0] : 0.0;
+  HMX_UNROLL
+  for (int st = 0; st < 5; ++st) {
+    const int m = 16 >> st, cnt = P >> st;  // values per lane before this step (0: one value, plain butterfly)
+    if (cnt > 1) {
+      const bool up = (lane & m) != 0;
+      HMX_UNROLL
+      for (int k = 0; k < (cnt >> 1); ++k) {
+        const double lo = w[k], hi = w[k + (cnt >> 1)];
+        w[k] = (up ? hi : lo) + lane_xor(up ? lo : hi, m);
+      }
+    } else {
+      w[0] += lane_xor(w[0], m);
+    }
+  }
+  return w[0];
+}
+
 template <int NV, int NW>
 HMX_DEV void block_sum(double (&v)[NV], double* buf) {
   const int lane = tid() & 31, warp = tid() >> 5;
-  HMX_UNROLL
-  for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
-  if (lane == 0) {
-    HMX_UNROLL
-    for (int k = 0; k < NV; ++k) buf[warp * NV + k] = v[k];
+  {
+    const double t = warp_sum_multi<NV>(v, lane);
+    const int k = warp_multi_index<NV>(lane);
+    if ((lane & (32 / WarpMulti<NV>::P - 1)) == 0 && k < NV) buf[warp * NV + k] = t;
   }
   sync();
   HMX_UNROLL
