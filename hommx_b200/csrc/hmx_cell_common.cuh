@@ -290,8 +290,10 @@ HMX_DEV double warp_sum_multi(const double (&v)[NV], int lane) {
   return w[0];
 }
 
+// first half of block_sum: the warp totals land in buf[warp * NV + k]; one BAR.SYNC.  For callers in which only a
+// few threads need the CTA totals (they add the NW partials in warp order themselves).
 template <int NV, int NW>
-HMX_DEV void block_sum(double (&v)[NV], double* buf) {
+HMX_DEV void block_partials(const double (&v)[NV], double* buf) {
   const int lane = tid() & 31, warp = tid() >> 5;
   {
     const double t = warp_sum_multi<NV>(v, lane);
@@ -299,6 +301,10 @@ HMX_DEV void block_sum(double (&v)[NV], double* buf) {
     if ((lane & (32 / WarpMulti<NV>::P - 1)) == 0 && k < NV) buf[warp * NV + k] = t;
   }
   sync();
+}
+template <int NV, int NW>
+HMX_DEV void block_sum(double (&v)[NV], double* buf) {
+  block_partials<NV, NW>(v, buf);
   HMX_UNROLL
   for (int k = 0; k < NV; ++k) {
     double s = 0.0;

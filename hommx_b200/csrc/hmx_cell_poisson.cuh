@@ -403,7 +403,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
             z[p * NRHS + q] += bq[j][p] * xq[j][q];
             z[NRHS * NRHS + p * NRHS + q] += xq[j][p] * rq[j][q];
           }
-      block_sum<2 * NRHS * NRHS, NW>(z, s_red + (red_flip ^= 1) * NW * L::NRED);
+      block_partials<2 * NRHS * NRHS, NW>(z, s_red + (red_flip ^= 1) * NW * L::NRED);  // warp partials only
       if (P.chi != nullptr) {  // correctors (BasePeriodicHMM.correctors, hmm.py:1211-1213), natural node order
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j) {
@@ -414,20 +414,36 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
           }
         }
       }
-      if (t_id == 0) {
-        double Ah[NRHS * NRHS];
+      // one thread per entry of A_hom, another warp for the macro gradients meanwhile, then one thread per entry of
+      // the macro element matrix (no serial chain on thread 0 while the CTA waits); the reduction buffer that the last
+      // block_sum did NOT use is free
+      constexpr int NBM = D + 1;
+      double* s_ah = s_red + (red_flip ^ 1) * NW * L::NRED;  // [D][D]
+      double* s_cm = s_ah + D * D;                           // [D][NBM] macro gradients, then |T|
+      static_assert(D * D + D * NBM + 1 <= NW * L::NRED, "epilogue scratch");
+      if (t_id < D * D) {
+        const int p = t_id / D, q = t_id - p * D;
+        double a = s_ck[sym_index(D, p, q)];
         HMX_UNROLL
-        for (int p = 0; p < D; ++p)
+        for (int k = 0; k < NA; ++k) a += s_ck[(1 + k) * NSYM + sym_index(D, p, q)] * smean[k];
+        // (z is indexed at run time: through the buffer the block_sum left the warp partials in)
+        const double* zb = s_red + red_flip * NW * L::NRED;
+        double z1 = 0.0, z2 = 0.0;
+        for (int w = 0; w < NW; ++w) {
+          z1 += zb[w * 2 * NRHS * NRHS + p * NRHS + q];
+          z2 += zb[w * 2 * NRHS * NRHS + NRHS * NRHS + p * NRHS + q];
+        }
+        s_ah[t_id] = a - z1 - z2;
+      }
+      if (t_id == NT - 1) {  // (the last warp: the first holds the A_hom threads)
+        if (P.S_loc != nullptr) {
+          double Cm[D][NBM];
+          s_cm[D * NBM] = macro_strain_matrix<D, 0>(verts, Cm);
           HMX_UNROLL
-          for (int q = 0; q < D; ++q) {
-            double a = s_ck[sym_index(D, p, q)];
+          for (int p = 0; p < D; ++p)
             HMX_UNROLL
-            for (int k = 0; k < NA; ++k) a += s_ck[(1 + k) * NSYM + sym_index(D, p, q)] * smean[k];
-            Ah[p * D + q] = a - z[p * NRHS + q] - z[NRHS * NRHS + p * NRHS + q];
-          }
-        if (P.A_hom != nullptr)
-          for (int k = 0; k < D * D; ++k) P.A_hom[pt * D * D + k] = Ah[k];
-        if (P.S_loc != nullptr) macro_element_matrix<D, 0>(verts, Ah, P.S_loc + pt * (D + 1) * (D + 1));
+            for (int i = 0; i < NBM; ++i) s_cm[p * NBM + i] = Cm[p][i];
+        }
         if (P.iters != nullptr) P.iters[pt] = it;
         if (P.work != nullptr) {
           unsigned long long tot = 0;
@@ -442,6 +458,17 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
             if (rz0[q] > P.atol * P.atol) worst = fmax(worst, sqrt(rz[q] / rz0[q]));
           P.resid[pt] = worst;
         }
+      }
+      sync();
+      if (P.A_hom != nullptr && t_id < D * D) P.A_hom[pt * D * D + t_id] = s_ah[t_id];
+      if (P.S_loc != nullptr && t_id < NBM * NBM) {
+        const int i = t_id / NBM, j = t_id - i * NBM;
+        double acc = 0.0;  // same summation order as macro_element_matrix
+        HMX_UNROLL
+        for (int p = 0; p < D; ++p)
+          HMX_UNROLL
+          for (int q2 = 0; q2 < D; ++q2) acc += s_cm[p * NBM + j] * s_ah[p * D + q2] * s_cm[q2 * NBM + i];
+        P.S_loc[pt * NBM * NBM + t_id] = s_cm[D * NBM] * acc;
       }
     }
     sync();  // shared memory is reused by the next macro point
