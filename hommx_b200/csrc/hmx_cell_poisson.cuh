@@ -84,14 +84,41 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
   const double vol = (D == 2 ? 0.5 : 1.0 / 6.0) * (D == 2 ? h * h : h * h * h) * (double)G::NLAYERS;
   int red_flip = 0;
 
+  // Node ownership.  TILED: a thread owns NPT CONSECUTIVE nodes along the last axis (a piece of a grid line; a warp
+  // holds 32 neighbouring lines, so every access is to consecutive doubles).  In K p a neighbouring line then serves
+  // two stencil directions of all NPT nodes from NPT + 1 loads (instead of 2 NPT), the own line needs two halo loads:
+  // 8 instead of 14 (3-D), 3 instead of 6 (2-D) loads of p per node, right-hand side and iteration -- the kernel is
+  // bound by shared-memory bandwidth (74 % of the pipe, profiles/r02_c3_poisson_v2_raw.txt).  Otherwise thread t owns
+  // nodes t, t + NT, ...
+  constexpr int LAST = 1 << (D - 1);  // stencil mask bit of the last axis
+  constexpr int NC = N / NM;          // nodes per layer of the last axis = number of grid lines (COLL = 0)
+#ifndef HMX_POISSON_TILED
+#define HMX_POISSON_TILED 1
+#endif
+  constexpr bool TILED = HMX_POISSON_TILED && COLL == 0 && NPT >= 2 && N % NT == 0 && NM % NPT == 0 && NT == NC * (NM / NPT);
+  const int line = TILED ? t_id % NC : 0, z0 = TILED ? (t_id / NC) * NPT : 0;
+  auto node = [&](int j) { return TILED ? line + NC * (z0 + j) : t_id + j * NT; };
+  int lnp[TILED ? LAST : 1], lnm[TILED ? LAST : 1], zoff[TILED ? NPT + 2 : 1];  // neighbour lines (layer 0), layers z0-1 .. z0+NPT
+  if (TILED) {
+    int c[3];
+    G::decode(line, c);
+    lnp[0] = lnm[0] = line;
+    HMX_UNROLL
+    for (int m = 1; m < LAST; ++m) {
+      lnp[TILED ? m : 0] = G::template shifted<1>(c, m);
+      lnm[TILED ? m : 0] = G::template shifted<-1>(c, m);
+    }
+    HMX_UNROLL
+    for (int k = 0; k < NPT + 2; ++k) zoff[TILED ? k : 0] = NC * ((z0 + k - 1 + NM) % NM);
+  }
   // neighbours of the owned nodes: they depend on the thread only, not on the macro point -- computing the
   // periodic wrap inside the PCG loop cost ~35 % of all issued instructions (profiles/r01_p2_inclusion16_raw.txt)
-  constexpr bool NBREG = NPT * 2 * NH <= 32;
+  constexpr bool NBREG = !TILED && NPT * 2 * NH <= 32;
   int nbp[NBREG ? NPT : 1][NBREG ? NH : 1], nbm[NBREG ? NPT : 1][NBREG ? NH : 1];
   if (NBREG) {
     HMX_UNROLL
     for (int j = 0; j < NPT; ++j) {
-      const int i = t_id + j * NT;
+      const int i = node(j);
       int c[3];
       G::decode(i < N ? i : 0, c);
       HMX_UNROLL
@@ -207,7 +234,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
     double bq[NPT][NRHS];
     HMX_UNROLL
     for (int j = 0; j < NPT; ++j) {
-      const int i = t_id + j * NT;
+      const int i = node(j);
       HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) bq[j][q] = 0.0;
       if (i < N) {
@@ -268,7 +295,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
     double dinv[NPT], kdiag[NPT];
     HMX_UNROLL
     for (int j = 0; j < NPT; ++j) {
-      const int i = t_id + j * NT;
+      const int i = node(j);
       dinv[j] = kdiag[j] = 0.0;
       if (i < N) {
         int c[3];
@@ -291,7 +318,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       for (int q = 0; q < NRHS; ++q) part[q] = 0.0;
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
-        const int i = t_id + j * NT;
+        const int i = node(j);
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q) {
           xq[j][q] = 0.0;
@@ -319,9 +346,73 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       double Ap[NPT][NRHS], pown[NPT][NRHS], pAp[NRHS];
       HMX_UNROLL
       for (int q = 0; q < NRHS; ++q) pAp[q] = 0.0;
+      if (TILED) {
+        const int i0 = line + zoff[TILED ? 1 : 0];  // first own node
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j)
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) {
+            pown[j][q] = s_p[q * N + i0 + NC * j];
+            Ap[j][q] = kdiag[j] * pown[j][q];
+          }
+        {  // own line, direction of the last axis: K[s][i] couples i and i + e, so node j uses k[j + 1] up, k[j] down
+          double kl[NPT + 1];
+          HMX_UNROLL
+          for (int k = 0; k <= NPT; ++k) kl[k] = s_K[(LAST - 1) * N + line + zoff[TILED ? k : 0]];
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) {
+            const double below = s_p[q * N + line + zoff[0]], above = s_p[q * N + line + zoff[TILED ? NPT + 1 : 0]];
+            HMX_UNROLL
+            for (int j = 0; j < NPT; ++j)
+              Ap[j][q] += kl[j + 1] * (j + 1 < NPT ? pown[j + 1 < NPT ? j + 1 : 0][q] : above) + kl[j] * (j > 0 ? pown[j > 0 ? j - 1 : 0][q] : below);
+          }
+        }
+        HMX_UNROLL
+        for (int m = 1; m < LAST; ++m) {
+          const int s0 = m - 1, s1 = (m | LAST) - 1;  // directions m (same layer) and m + e_last (next layer)
+          {  // neighbours i + m, i + m + e_last: entries K[s][i] of the own nodes, line lnp[m], layers z .. z + 1
+            const int ln = lnp[TILED ? m : 0];
+            double k0[NPT], k1[NPT];
+            HMX_UNROLL
+            for (int j = 0; j < NPT; ++j) {
+              k0[j] = s_K[s0 * N + i0 + NC * j];
+              k1[j] = s_K[s1 * N + i0 + NC * j];
+            }
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) {
+              double v[NPT + 1];
+              HMX_UNROLL
+              for (int k = 0; k <= NPT; ++k) v[k] = s_p[q * N + ln + zoff[TILED ? k + 1 : 0]];
+              HMX_UNROLL
+              for (int j = 0; j < NPT; ++j) Ap[j][q] += k0[j] * v[j] + k1[j] * v[j + 1];
+            }
+          }
+          {  // neighbours i - m, i - m - e_last: entries K[s][neighbour], line lnm[m], layers z .. z - 1
+            const int ln = lnm[TILED ? m : 0];
+            double k0[NPT], k1[NPT];
+            HMX_UNROLL
+            for (int j = 0; j < NPT; ++j) {
+              k0[j] = s_K[s0 * N + ln + zoff[TILED ? j + 1 : 0]];
+              k1[j] = s_K[s1 * N + ln + zoff[TILED ? j : 0]];
+            }
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) {
+              double v[NPT + 1];
+              HMX_UNROLL
+              for (int k = 0; k <= NPT; ++k) v[k] = s_p[q * N + ln + zoff[TILED ? k : 0]];
+              HMX_UNROLL
+              for (int j = 0; j < NPT; ++j) Ap[j][q] += k0[j] * v[j + 1] + k1[j] * v[j];
+            }
+          }
+        }
+        HMX_UNROLL
+        for (int j = 0; j < NPT; ++j)
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) pAp[q] += pown[j][q] * Ap[j][q];
+      } else {
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {
-        const int i = t_id + j * NT;
+        const int i = node(j);
         HMX_UNROLL
         for (int q = 0; q < NRHS; ++q) Ap[j][q] = pown[j][q] = 0.0;
         if (i < N) {
@@ -344,6 +435,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
           HMX_UNROLL
           for (int q = 0; q < NRHS; ++q) pAp[q] += pown[j][q] * Ap[j][q];
         }
+      }
       }
       block_sum<NRHS, NW>(pAp, s_red + (red_flip ^= 1) * NW * L::NRED);
       double alpha[NRHS], part[NRHS];
@@ -378,7 +470,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       if (any) {
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j) {
-          const int i = t_id + j * NT;
+          const int i = node(j);
           if (i < N) {
             HMX_UNROLL
             for (int q = 0; q < NRHS; ++q)
@@ -407,7 +499,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       if (P.chi != nullptr) {  // correctors (BasePeriodicHMM.correctors, hmm.py:1211-1213), natural node order
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j) {
-          const int i = t_id + j * NT;
+          const int i = node(j);
           if (i < N) {
             HMX_UNROLL
             for (int q = 0; q < NRHS; ++q) P.chi[((size_t)pt * NRHS + q) * N + i] = xq[j][q];
