@@ -42,7 +42,8 @@ struct PoissonLayout {
   static constexpr int NRED = 2 * NRHS * NRHS > NA1 ? 2 * NRHS * NRHS : NA1;
   // offsets in doubles
   static constexpr int o_red = 0;                                    // 2 buffers
-  static constexpr int o_bk = o_red + 2 * NW * NRED;                 // [(1+NA)][NSYM]   M^T C_k M
+  static constexpr int o_vt = o_red + 2 * NW * NRED;                 // [(D+1)][3] macro cell vertices (for the epilogue)
+  static constexpr int o_bk = o_vt + (D + 1) * 3;                    // [(1+NA)][NSYM]   M^T C_k M
   static constexpr int o_rk = o_bk + (1 + NA) * NSYM;                // [(1+NA)][D][D]   M^T C_k
   static constexpr int o_ck = o_rk + (1 + NA) * D * D;               // [(1+NA)][NSYM]   C_k
   static constexpr int o_kap = o_ck + (1 + NA) * NSYM;               // [(1+NA)][T][NPAIR]
@@ -69,6 +70,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
 
   double* sm = dyn_smem();
   double* s_red = sm + L::o_red;
+  double* s_vt = sm + L::o_vt;
   double* s_bk = sm + L::o_bk;
   double* s_rk = sm + L::o_rk;
   double* s_ck = sm + L::o_ck;
@@ -131,8 +133,15 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
 
   for (long long pt = bid(); pt < P.n_pts; pt += nblocks()) {
     // ---- 0. macro point, per-point constants, stratification Jacobian (registers) ----
-    double xm[3], verts[(D + 1) * 3];
-    macro_point<D>(P, pt, xm, verts);
+    double xm[3];
+    {  // the vertices are needed again in the epilogue only: parked in shared memory, not in 24 registers
+      double verts[(D + 1) * 3];
+      macro_point<D>(P, pt, xm, verts);
+      if (t_id == NT - 1) {
+        HMX_UNROLL
+        for (int k = 0; k < (D + 1) * 3; ++k) s_vt[k] = verts[k];
+      }
+    }
     double pc[NPC1];
     CO::point_consts(xm, pc);
     double M[D * D];  // M[p*D+i] = d theta_i / d x_p  (hmm.py:756-757)
@@ -231,48 +240,81 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
     sync();
 
     // ---- 2c. half stencil and load vectors of the owned nodes ----
+    // The tables kap / beta are the same for every node (structured mesh): each entry is loaded ONCE per thread and
+    // used for (up to) JB owned nodes, whose accumulators live in registers together -- the per-node order of the
+    // sums is (t, a, b) as in the reference assembly.  (One node at a time, this phase issued more shared-memory
+    // loads than all PCG iterations of a C3 cell: 168 per node.)
     double bq[NPT][NRHS];
+    constexpr int JB = NPT < 4 ? NPT : 4;
     HMX_UNROLL
-    for (int j = 0; j < NPT; ++j) {
-      const int i = node(j);
+    for (int j0 = 0; j0 < NPT; j0 += JB) {
+      double acc[JB][NH];
+      int cj[JB][3];
+      bool valid[JB];
       HMX_UNROLL
-      for (int q = 0; q < NRHS; ++q) bq[j][q] = 0.0;
-      if (i < N) {
-        int c[3];
-        G::decode(i, c);
-        double acc[NH];
+      for (int jj = 0; jj < JB; ++jj) {
+        const int j = j0 + jj < NPT ? j0 + jj : NPT - 1;
+        const int i = node(j);
+        valid[jj] = j0 + jj < NPT && i < N;
+        G::decode(valid[jj] ? i : 0, cj[jj]);
         HMX_UNROLL
-        for (int s = 0; s < NH; ++s) acc[s] = 0.0;
+        for (int q = 0; q < NRHS; ++q) bq[j][q] = 0.0;
         HMX_UNROLL
-        for (int t = 0; t < T; ++t) {
+        for (int s = 0; s < NH; ++s) acc[jj][s] = 0.0;
+      }
+      HMX_UNROLL
+      for (int t = 0; t < T; ++t) {
+        HMX_UNROLL
+        for (int a = 0; a <= D; ++a) {
+          double be[NA1][NRHS], sa[JB][NA1];
           HMX_UNROLL
-          for (int a = 0; a <= D; ++a) {
+          for (int k = 0; k < NA; ++k)
+            HMX_UNROLL
+            for (int q = 0; q < NRHS; ++q) be[k][q] = s_beta[((k * T + t) * (D + 1) + a) * NRHS + q];
+          HMX_UNROLL
+          for (int jj = 0; jj < JB; ++jj) {
             // node i is vertex a of the type-t element of cube o = c - P(t,a)
             int o[3];
-            G::template shift_coords<-1>(c, kuhn_pmask<D>(t, a), o);
+            G::template shift_coords<-1>(cj[jj], kuhn_pmask<D>(t, a), o);
             const int ro = AI::ridx(o);
-            double sa[NA1];
             HMX_UNROLL
-            for (int k = 0; k < NA; ++k) sa[k] = s_atoms[(k * T + t) * NRC + ro];
-            HMX_UNROLL
-            for (int k = 0; k < NA; ++k)
+            for (int k = 0; k < NA; ++k) sa[jj][k] = s_atoms[(k * T + t) * NRC + ro];
+            if (j0 + jj < NPT) {
               HMX_UNROLL
-              for (int q = 0; q < NRHS; ++q) bq[j][q] += s_beta[((k * T + t) * (D + 1) + a) * NRHS + q] * sa[k];
+              for (int k = 0; k < NA; ++k)
+                HMX_UNROLL
+                for (int q = 0; q < NRHS; ++q) bq[j0 + jj < NPT ? j0 + jj : 0][q] += be[k][q] * sa[jj][k];
+            }
+          }
+          HMX_UNROLL
+          for (int b = a + 1; b <= D; ++b) {
+            // pair index of (a,b) in the a<b enumeration
+            const int pr = a * D - a * (a - 1) / 2 + (b - a - 1);
+            const int slot = (kuhn_pmask<D>(t, b) & ~kuhn_pmask<D>(t, a)) - 1;
+            const double k0 = s_kap[(0 * T + t) * NPAIR + pr];
+            double kk[NA1];
             HMX_UNROLL
-            for (int b = a + 1; b <= D; ++b) {
-              // pair index of (a,b) in the a<b enumeration
-              const int pr = a * D - a * (a - 1) / 2 + (b - a - 1);
-              const int slot = (kuhn_pmask<D>(t, b) & ~kuhn_pmask<D>(t, a)) - 1;
-              double v = s_kap[(0 * T + t) * NPAIR + pr];
+            for (int k = 0; k < NA; ++k) kk[k] = s_kap[((1 + k) * T + t) * NPAIR + pr];
+            HMX_UNROLL
+            for (int jj = 0; jj < JB; ++jj) {
+              double v = k0;
               HMX_UNROLL
-              for (int k = 0; k < NA; ++k) v += s_kap[((1 + k) * T + t) * NPAIR + pr] * sa[k];
-              acc[slot] += v;
+              for (int k = 0; k < NA; ++k) v += kk[k] * sa[jj][k];
+              acc[jj][slot] += v;
             }
           }
         }
-        HMX_UNROLL
-        for (int s = 0; s < NH; ++s) s_K[s * N + i] = acc[s];
       }
+      HMX_UNROLL
+      for (int jj = 0; jj < JB; ++jj)
+        if (valid[jj]) {
+          const int i = node(j0 + jj);
+          HMX_UNROLL
+          for (int s = 0; s < NH; ++s) s_K[s * N + i] = acc[jj][s];
+        } else if (j0 + jj < NPT) {
+          HMX_UNROLL
+          for (int q = 0; q < NRHS; ++q) bq[j0 + jj < NPT ? j0 + jj : 0][q] = 0.0;  // (a slot past the last node)
+        }
     }
     // atom means for <A> (every thread gets them)
     double smean[NA1];
@@ -530,7 +572,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       if (t_id == NT - 1) {  // (the last warp: the first holds the A_hom threads)
         if (P.S_loc != nullptr) {
           double Cm[D][NBM];
-          s_cm[D * NBM] = macro_strain_matrix<D, 0>(verts, Cm);
+          s_cm[D * NBM] = macro_strain_matrix<D, 0>(s_vt, Cm);  // (written by this thread)
           HMX_UNROLL
           for (int p = 0; p < D; ++p)
             HMX_UNROLL

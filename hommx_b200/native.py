@@ -304,6 +304,11 @@ def default_min_blocks(dim, kind, n, threads, coll=0, vglob=0):
         # 3 CTAs/SM at 96 registers 119k, 2 at 168 registers 183k, 1 at 254 registers 167k cell solves/s);
         # with the vectors in L2 a second CTA only adds L2 contention (n = 10: 5.8k vs 4.5k)
         return 1 if vglob else max(1, 65536 // (threads * 168))
+    if kind == POISSON and dim == 3 and coll == 0 and threads <= 128:
+        # full 3-D Poisson cells with 4+ nodes per thread: the line-tiled K p keeps NPT + 1 neighbour values of three
+        # right-hand sides in flight; measured at 8^3 / 128 threads: 3 CTAs at 168 registers 24.3M, 4 at 128 registers
+        # (spilling) 22.7M cell solves/s; 64 threads: 6 CTAs 18.4M, 8 CTAs 16.6M
+        return max(1, min(8, 65536 // (threads * 168)))
     # (elasticity: the small / axis-collapsed kernels; measured on the collapsed C4 kernel: 215k -> 276k cell
     # solves/s going from 2 to 4-5 CTAs per SM)
     return max(1, min(8, 65536 // (threads * 112)))

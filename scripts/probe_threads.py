@@ -1,4 +1,4 @@
-"""An elasticity case at other thread counts (python scripts/probe_threads.py <case>[:n] <npts> 192 384:1 192:2 ... (threads[:min_blocks])."""
+"""A parity case at other thread counts (python scripts/probe_threads.py <case>[:n] <npts> 192 384:1 192:2 ... (threads[:min_blocks])."""
 import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 import numpy as np, torch
 import cases as K
@@ -10,7 +10,8 @@ if nn: case = dataclasses.replace(case, n=int(nn))
 prog = K.program(case); qp, qw = K.tables(case, prog)
 npts = int(sys.argv[2])
 rng = np.random.default_rng(0); x = rng.uniform(0, 1, (npts, 3))
-xd = torch.tensor(x, device='cuda'); A = torch.empty((npts, 6, 6), device='cuda', dtype=torch.float64)
+if case.dim == 2: x[:, 2] = 0.0
+xd = torch.tensor(x, device='cuda'); A = torch.empty((npts, prog.n_rhs, prog.n_rhs), device='cuda', dtype=torch.float64)
 ref = None
 for arg in sys.argv[3:] or ['384', '192']:
     nt, _, mb = arg.partition(':')
