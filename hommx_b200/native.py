@@ -297,8 +297,7 @@ def _extra_flags():
 
 def default_min_blocks(dim, kind, n, threads, coll=0, vglob=0):
     """__launch_bounds__ minimum of resident CTAs per SM (caps registers per thread).  The Poisson
-    kernels are latency-bound (few PCG iterations, ~25 barriers per point): two or more CTAs per SM
-    hide it; 128 registers per thread still compile without spills."""
+    kernels run few PCG iterations with ~25 barriers per point: two or more CTAs per SM hide them."""
     if kind != POISSON and dim == 3 and coll == 0 and threads >= 32 * 6:
         # full 3-D elasticity cells: the sweep wants 168 registers per thread (n = 6 at 192 threads, measured:
         # 3 CTAs/SM at 96 registers 119k, 2 at 168 registers 183k, 1 at 254 registers 167k cell solves/s);
