@@ -97,9 +97,11 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
 #ifndef HMX_POISSON_TILED
 #define HMX_POISSON_TILED 1
 #endif
-  constexpr bool TILED = HMX_POISSON_TILED && COLL == 0 && NPT >= 2 && N % NT == 0 && NM % NPT == 0 && NT == NC * (NM / NPT);
-  const int line = TILED ? t_id % NC : 0, z0 = TILED ? (t_id / NC) * NPT : 0;
-  auto node = [&](int j) { return TILED ? line + NC * (z0 + j) : t_id + j * NT; };
+  constexpr int NACT = NPT > 0 && NM % NPT == 0 ? NC * (NM / NPT) : NT + 1;  // threads that own a line piece
+  constexpr bool TILED = HMX_POISSON_TILED && COLL == 0 && NPT >= 2 && NM % NPT == 0 && NACT <= NT;
+  const bool own = !TILED || t_id < NACT;  // (NT is NACT rounded up to whole warps: the last threads own nothing)
+  const int line = TILED ? (own ? t_id : 0) % NC : 0, z0 = TILED ? ((own ? t_id : 0) / NC) * NPT : 0;
+  auto node = [&](int j) { return TILED ? (own ? line + NC * (z0 + j) : N) : t_id + j * NT; };
   int lnp[TILED ? LAST : 1], lnm[TILED ? LAST : 1], zoff[TILED ? NPT + 2 : 1];  // neighbour lines (layer 0), layers z0-1 .. z0+NPT
   if (TILED) {
     int c[3];
@@ -450,7 +452,10 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
         HMX_UNROLL
         for (int j = 0; j < NPT; ++j)
           HMX_UNROLL
-          for (int q = 0; q < NRHS; ++q) pAp[q] += pown[j][q] * Ap[j][q];
+          for (int q = 0; q < NRHS; ++q) {
+            if (NACT < NT && !own) pown[j][q] = Ap[j][q] = 0.0;  // (a thread without nodes read thread 0's line)
+            pAp[q] += pown[j][q] * Ap[j][q];
+          }
       } else {
       HMX_UNROLL
       for (int j = 0; j < NPT; ++j) {

@@ -257,8 +257,9 @@ def cluster_size(prog, n):
     return 0
 
 
-def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
-    """Threads per CTA for the cell kernel of an n^dim micro mesh (minus its collapsed axes)."""
+def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0, prog=None):
+    """Threads per CTA for the cell kernel of an n^dim micro mesh (minus its collapsed axes).  ``prog`` (optional)
+    lets the Poisson choice see how much shared memory the atoms of the coefficient take."""
     N = n ** (dim - bin(coll).count("1"))
     if kind != POISSON and variant == DENSE:
         return 256  # 16 x 16 owners of the register tile
@@ -267,6 +268,27 @@ def default_threads(dim, kind, n, variant=MATRIX_FREE, coll=0):
         # (measured on B200, scripts/probe_occ.py: C3 12.2M -> 19.0M, C2 7.0M -> 11.6M points/s)
         nt = -(-N // 4)
         nt = max(64, min(1024, 32 * (-(-nt // 32))))
+        if prog is not None and not vectors_in_l2(prog, n, coll):
+            # many atoms on a fully y-dependent coefficient: shared memory, not registers, limits the CTAs per SM, and
+            # the atom means (one element per thread) dominate -- 16 warps per SM at least (measured, 4 atoms at 8^3,
+            # one CTA per SM: 128 threads 133k, 256 threads 236k, 512 threads 338k cell solves/s)
+            ndep = bin(prog.ydep & ((1 << dim) - 1)).count("1")
+            atoms = max(1, prog.natoms) * (2 if dim == 2 else 6) * n**ndep
+            smem = 8 * ((2**dim - 1) * N + max(dim * N, atoms) + 512)
+            ctas = max(1, SMEM_LIMIT // smem)
+            if atoms > dim * N and ctas * nt < 512 and ctas <= 2:
+                return min(512, 32 * (-(-512 // (32 * ctas))))
+        if coll == 0 and dim >= 2:
+            # ... and a count with which the kernel can give every thread a piece of a grid line (PoissonLayout
+            # TILED: n divisible by the nodes per thread; the line pieces rounded up to whole warps).  At most 512
+            # threads: more nodes per thread at >= 128 registers beat more threads that spill (measured, 48^2: 384
+            # threads x 6 nodes 2.49M, 576 x 4 1.58M-1.78M cell solves/s; 64^2: 512 x 8 0.73M-0.75M, 1024 x 4 0.56M-0.58M;
+            # 5 nodes per thread at 10^3: 0.86x of 256 threads without line pieces)
+            for npt in (4, 3, 6, 8):
+                if n % npt == 0:
+                    cand = 32 * (-(-(N // n) * (n // npt) // 32))
+                    if 64 <= cand <= 512 and -(-N // cand) == npt:
+                        return cand
         return nt
     nrhs = dim * (dim + 1) // 2
     ncol = 2 ** (dim - bin(coll).count("1"))
@@ -387,7 +409,7 @@ def resolve(prog, n, threads=None, min_blocks=None, variant=None, collapse=False
         if cl < 2 or n % cl:
             raise HmxError(f"an {n}^3 cell cannot be split into z-slabs over a thread-block cluster")
         return threads or cluster_threads(prog, n, cl), 1, variant, 0
-    threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll)
+    threads = threads or default_threads(prog.dim, prog.kind, n, variant, coll, prog)
     vg = vectors_in_l2(prog, n, coll) if variant == MATRIX_FREE else 0
     min_blocks = min_blocks or (1 if variant == DENSE else default_min_blocks(prog.dim, prog.kind, n, threads, coll, vg))
     return threads, min_blocks, variant, coll

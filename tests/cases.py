@@ -49,6 +49,9 @@ CASES = [
     Case("p3_smooth_n8_c3", 3, 0, 8, "smooth_sin"),  # BASELINE config 3
     Case("p3_fulltensor_shear_n5", 3, 0, 5, "full_tensor_3d", "dtheta_shear_3d"),
     Case("p3_fulltensor_n6", 3, 0, 6, "full_tensor_3d", threads=64),
+    Case("p3_smooth_n6_lines", 3, 0, 6, "smooth_sin"),  # default threads: 96, of which 72 own a piece of a grid line
+    Case("p2_inclusion_n24_lines", 2, 0, 24, "inclusion", "dtheta_inclusion"),  # 160 threads, 144 line pieces
+    Case("p3_smooth_n10_lines", 3, 0, 10, "smooth_sin", threads=224, heavy=True),  # 5 nodes per thread: two register chunks in the set-up
     Case("p3_smooth_n12", 3, 0, 12, "smooth_sin", heavy=True),
     Case("p2_inclusion_n64", 2, 0, 64, "inclusion", heavy=True),
     Case("p3_fulltensor_n10_l2", 3, 0, 10, "full_tensor_3d", heavy=True),  # 4 atoms x 6000 elements: atoms in L2
