@@ -246,7 +246,7 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
     // used for (up to) JB owned nodes, whose accumulators live in registers together -- the per-node order of the
     // sums is (t, a, b) as in the reference assembly.  (One node at a time, this phase issued more shared-memory
     // loads than all PCG iterations of a C3 cell: 168 per node.)
-    double bq[NPT][NRHS];
+    double bq[NPT][NRHS], kown[NPT];  // kown: sum of the node's own half-stencil entries (for the diagonal)
     constexpr int JB = NPT < 4 ? NPT : 4;
     HMX_UNROLL
     for (int j0 = 0; j0 < NPT; j0 += JB) {
@@ -311,9 +311,15 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       for (int jj = 0; jj < JB; ++jj)
         if (valid[jj]) {
           const int i = node(j0 + jj);
+          double ks = 0.0;
           HMX_UNROLL
-          for (int s = 0; s < NH; ++s) s_K[s * N + i] = acc[jj][s];
+          for (int s = 0; s < NH; ++s) {
+            s_K[s * N + i] = acc[jj][s];
+            ks += acc[jj][s];
+          }
+          kown[j0 + jj < NPT ? j0 + jj : 0] = ks;
         } else if (j0 + jj < NPT) {
+          kown[j0 + jj < NPT ? j0 + jj : 0] = 0.0;
           HMX_UNROLL
           for (int q = 0; q < NRHS; ++q) bq[j0 + jj < NPT ? j0 + jj : 0][q] = 0.0;  // (a slot past the last node)
         }
@@ -344,9 +350,14 @@ HMX_DEV void poisson_cell_body(const CellParams& P) {
       if (i < N) {
         int c[3];
         G::decode(i, c);
-        double d = 0.0;
+        double d = -kown[j];  // own entries from registers, the neighbours' entries towards this node from memory
         HMX_UNROLL
-        for (int s = 0; s < NH; ++s) d -= s_K[s * N + i] + s_K[s * N + G::template shifted<-1>(c, s + 1)];
+        for (int s = 0; s < NH; ++s) {
+          // neighbour i - (s + 1): with line pieces, line lnm[mask without the last axis], layer z or z - 1
+          const int im = TILED ? lnm[TILED ? ((s + 1) & (LAST - 1)) : 0] + zoff[TILED ? (((s + 1) & LAST) ? j : j + 1) : 0]
+                               : G::template shifted<-1>(c, s + 1);
+          d -= s_K[s * N + im];
+        }
         kdiag[j] = d;
         dinv[j] = d != 0.0 ? 1.0 / d : 0.0;
       }
