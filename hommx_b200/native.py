@@ -238,7 +238,7 @@ def cluster_smem_bytes(prog, n, cl):
         cbuf = max(3 * pad + 2, 6 * ncd) + 2
     work = max(pz * n * 18, 6 * ncd + 6 * nblk + 2, cbuf, (nt // 36) * 36, 110)
     ntri = ncd * (ncd + 1) // 2 if two else 0
-    doubles = 4 + (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
+    doubles = 12 + (nt // 32) * 8 + cl * 8 + cl * nrec + 8 + 6 * ncd + work + 1 + ntri + 1 + npb * 18 + 63 * nown + 36 * npl
     if two and 8 * doubles > SMEM_LIMIT:  # the inverse coarse matrix moves to the global scratch (ClusterLayout::EIG)
         doubles -= ntri
     return 8 * doubles
